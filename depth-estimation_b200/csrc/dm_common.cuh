@@ -1,0 +1,153 @@
+// dm_common.cuh -- shared host/device plumbing of libdepthmatch (sm_100a only).
+//
+// Context object, error reporting, host<->device staging, and the small PTX
+// wrappers (mbarrier, TMA bulk-tensor copy) the kernels use.  No torch types, no
+// CPU fallback: every entry point fails with DM_ERR_CUDA when no device is there.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/depthmatch.h"
+
+namespace dm {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define DM_CUDA(expr)                                                       \
+  do {                                                                      \
+    cudaError_t _e = (expr);                                                \
+    if (_e != cudaSuccess) return ::dm::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define DM_CHECK(expr)                \
+  do {                                \
+    int _s = (expr);                  \
+    if (_s != DM_OK) return _s;       \
+  } while (0)
+
+#define DM_REQUIRE(cond, ...)         \
+  do {                                \
+    if (!(cond)) {                    \
+      ::dm::set_error(__VA_ARGS__);   \
+      return DM_ERR_INVALID;          \
+    }                                 \
+  } while (0)
+
+// ---------------------------------------------------------------- context
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+};
+
+}  // namespace dm
+
+struct dm_ctx {
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  dm::Arena arena;       // device scratch + staging, bump-allocated per call
+  int64_t launches = 0;  // kernels launched through this context
+  // pending device->host copies of the current call
+  struct Pending {
+    void *host;
+    const void *dev;
+    size_t bytes;
+  };
+  std::vector<Pending> pending;
+  bool call_has_host = false;
+};
+
+namespace dm {
+
+enum class PtrKind { Device, Host };
+PtrKind classify(const void *p);
+
+// Per-call staging helper.  begin() resets the arena; in()/out() return a device
+// pointer for a user pointer (copying host data in, registering host outputs for
+// copy-back); finish() copies outputs back and synchronises when any host pointer
+// was involved.
+struct Call {
+  dm_ctx *ctx;
+  explicit Call(dm_ctx *c);
+  int alloc(void **dptr, size_t bytes);  // device scratch, 256-byte aligned
+  int in(const void *user, size_t bytes, const void **dptr);
+  // like in() but a pitched 2D copy: rows of row_bytes, user pitch -> dense device rows
+  int out(void *user, size_t bytes, void **dptr, bool preload = false);
+  int finish();
+};
+
+int ensure_arena(dm_ctx *ctx, size_t bytes);
+
+inline void count_launch(dm_ctx *ctx, int n = 1) { ctx->launches += n; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda, so the
+// library still loads on a box without a driver).
+int encode_tensor_map_4d(CUtensorMap *map, const float *base, const uint64_t dims[4],
+                         const uint64_t strides_bytes[3], const uint32_t box[4]);
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- device PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 4-D tiled TMA load global -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#endif
+
+}  // namespace dm

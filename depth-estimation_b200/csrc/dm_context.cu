@@ -1,0 +1,258 @@
+// dm_context.cu -- context, error reporting, pointer classification and staging.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "dm_common.cuh"
+
+namespace dm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return DM_ERR_CUDA;
+}
+
+PtrKind classify(const void *p) {
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return PtrKind::Host;
+  }
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return PtrKind::Device;
+  return PtrKind::Host;
+}
+
+int ensure_arena(dm_ctx *ctx, size_t bytes) {
+  if (ctx->arena.cap >= bytes) return DM_OK;
+  // growing invalidates earlier pointers of this call: callers size before use
+  DM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->arena.base) DM_CUDA(cudaFree(ctx->arena.base));
+  ctx->arena.base = nullptr;
+  ctx->arena.cap = 0;
+  size_t want = bytes + (bytes >> 2) + (1u << 20);
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("out of device memory allocating %zu bytes of workspace", want);
+    return DM_ERR_NOMEM;
+  }
+  ctx->arena.base = static_cast<char *>(p);
+  ctx->arena.cap = want;
+  return DM_OK;
+}
+
+Call::Call(dm_ctx *c) : ctx(c) {
+  ctx->arena.used = 0;
+  ctx->pending.clear();
+  ctx->call_has_host = false;
+}
+
+// The arena is a bump allocator.  To keep pointers stable we never grow it in the
+// middle of a call once something was handed out: instead a chain of extra
+// cudaMalloc'd blocks is avoided by letting the first allocation of a call that
+// does not fit trigger a grow only when nothing is live; otherwise we fall back to
+// a dedicated allocation that is released at finish().
+struct Extra {
+  void *p;
+};
+static thread_local std::vector<void *> g_extra;
+
+int Call::alloc(void **dptr, size_t bytes) {
+  const size_t aligned = (bytes + 255) & ~size_t(255);
+  if (ctx->arena.used + aligned > ctx->arena.cap) {
+    if (ctx->arena.used == 0) {
+      DM_CHECK(ensure_arena(ctx, aligned));
+    } else {
+      void *p = nullptr;
+      cudaError_t e = cudaMalloc(&p, aligned);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("out of device memory allocating %zu bytes", aligned);
+        return DM_ERR_NOMEM;
+      }
+      g_extra.push_back(p);
+      *dptr = p;
+      return DM_OK;
+    }
+  }
+  *dptr = ctx->arena.base + ctx->arena.used;
+  ctx->arena.used += aligned;
+  return DM_OK;
+}
+
+int Call::in(const void *user, size_t bytes, const void **dptr) {
+  if (classify(user) == PtrKind::Device) {
+    *dptr = user;
+    return DM_OK;
+  }
+  void *d = nullptr;
+  DM_CHECK(alloc(&d, bytes));
+  DM_CUDA(cudaMemcpyAsync(d, user, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->call_has_host = true;
+  *dptr = d;
+  return DM_OK;
+}
+
+int Call::out(void *user, size_t bytes, void **dptr, bool preload) {
+  if (classify(user) == PtrKind::Device) {
+    *dptr = user;
+    return DM_OK;
+  }
+  void *d = nullptr;
+  DM_CHECK(alloc(&d, bytes));
+  if (preload) DM_CUDA(cudaMemcpyAsync(d, user, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->pending.push_back({user, d, bytes});
+  ctx->call_has_host = true;
+  *dptr = d;
+  return DM_OK;
+}
+
+int Call::finish() {
+  int rc = DM_OK;
+  for (auto &p : ctx->pending) {
+    cudaError_t e = cudaMemcpyAsync(p.host, p.dev, p.bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess && rc == DM_OK) rc = cuda_fail(e, "copy-back", __FILE__, __LINE__);
+  }
+  ctx->pending.clear();
+  if (ctx->call_has_host || !g_extra.empty()) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess && rc == DM_OK) rc = cuda_fail(e, "stream synchronize", __FILE__, __LINE__);
+  }
+  for (void *p : g_extra) cudaFree(p);
+  g_extra.clear();
+  if (rc == DM_OK) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch", __FILE__, __LINE__);
+  }
+  return rc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tensor_map_4d(CUtensorMap *map, const float *base, const uint64_t dims[4],
+                         const uint64_t strides_bytes[3], const uint32_t box[4]) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return DM_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  cuuint64_t gdims[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t gbox[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), gdims, gstr,
+                  gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+              (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)dims[2], (unsigned long long)dims[3], box[0], box[1], box[2],
+              box[3]);
+    return DM_ERR_CUDA;
+  }
+  return DM_OK;
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" {
+
+int dm_version(void) { return DM_VERSION; }
+
+const char *dm_last_error(void) { return dm::g_err; }
+
+int dm_create(int device, dm_ctx **out) {
+  DM_REQUIRE(out != nullptr, "dm_create: ctx pointer is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("dm_create: no CUDA device (%s); libdepthmatch has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return DM_ERR_CUDA;
+  }
+  DM_REQUIRE(device >= 0 && device < ndev, "dm_create: device %d out of range [0,%d)", device, ndev);
+  DM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("dm_create: device %d is sm_%d%d; this library holds sm_100a code only", device,
+              prop.major, prop.minor);
+    return DM_ERR_UNSUPPORTED;
+  }
+  dm_ctx *ctx = new dm_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return DM_OK;
+}
+
+int dm_destroy(dm_ctx *ctx) {
+  if (!ctx) return DM_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->arena.base) cudaFree(ctx->arena.base);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return DM_OK;
+}
+
+int dm_synchronize(dm_ctx *ctx) {
+  DM_REQUIRE(ctx != nullptr, "dm_synchronize: ctx is NULL");
+  DM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DM_OK;
+}
+
+int dm_set_stream(dm_ctx *ctx, void *cuda_stream) {
+  DM_REQUIRE(ctx != nullptr, "dm_set_stream: ctx is NULL");
+  DM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return DM_OK;
+}
+
+void *dm_get_stream(dm_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+int dm_host_alloc(void **ptr, size_t bytes) {
+  DM_REQUIRE(ptr != nullptr, "dm_host_alloc: ptr is NULL");
+  DM_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return DM_OK;
+}
+
+int dm_host_free(void *ptr) {
+  if (ptr) DM_CUDA(cudaFreeHost(ptr));
+  return DM_OK;
+}
+
+int64_t dm_launch_count(dm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

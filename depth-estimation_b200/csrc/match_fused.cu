@@ -1,0 +1,629 @@
+// match_fused.cu -- K1+K2: cost volume, softmax statistics, winner-take-all argmax,
+// thresholded score extraction and soft/sub-pixel mean in ONE pass; the
+// H1 x W1 x maxh x maxw volume never exists in HBM.
+//
+// Reference semantics being fused (all per output pixel, window entries k in scan
+// order dy-major, 1-based):
+//   v_k   = sum_c (in1[c,y,x] - in2[c,y+dy,x+dx])^2     nn.SpatialMatching  (opticalflow_model.lua:93)
+//   p_k   = exp(min_v - v_k) / sum_j exp(min_v - v_j)   Minus + SoftMax     (:94-109)
+//   index = first argmax_k p_k, middle-index tie rule   getOutputConfidences (:153-161)
+//   thr   = extractOutput(p, 0.11)                      extract_output.cpp:63-155
+//   y,x   = sum_k p_k*row_k, sum_k p_k*col_k            OutputExtractor.lua:21-35
+//   flow  = (row,col) - ceil(max/2), pasted in a canvas processOutput        (:201-252)
+//
+// Numerics: SSD in fp32, channel-ascending, FMA-contracted unless DM_FLAG_EXACT_SSD;
+// the softmax runs online (flash-style running minimum) with ex2.approx, so
+// probabilities agree with the two-pass CPU path to ~1e-6 relative, not bit-wise.
+#include "match_kernels.cuh"
+
+namespace dm {
+
+constexpr int kBarBytes = 128;  // room for the kNSlot mbarriers, keeps what follows 16-byte aligned
+constexpr int kNC = 9;  // candidate entries per pixel: at most 9 probabilities can exceed 0.1
+
+struct ExtractParams {
+  SweepGeom g;
+  unsigned flags;
+  double thr;         // probability threshold of extractOutput
+  float cand_margin;  // ln(1/thr) + slack: v_k < min + margin is necessary for p_k > thr
+  int M;              // 8 if thr < 0.2 else 4 (extract_output.cpp:82-84)
+  int mid_dy, mid_dx, middle;  // zero-flow entry (0-based dy,dx; 1-based index)
+  int cy, cx;                  // ceil(maxh/2), ceil(maxw/2)
+  int h_img, w_img, hoff, woff;
+  long long *index;
+  float *min_ssd, *pmax, *flow_full;
+  long long *index_thr;
+  float *score_thr, *soft_yx;
+  unsigned long long *n_untouched;
+  float *cand_v;  // [grid][256][P][kNC]
+  int *cand_k;
+};
+
+// sorting networks of the reference (extract_output.cpp:27-33, :35-61), same order
+__device__ __constant__ unsigned char kNet4[5][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}, {1, 2}};
+__device__ __constant__ unsigned char kNet8[19][2] = {
+    {0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {1, 2}, {5, 6},
+    {0, 4}, {3, 7}, {1, 5}, {2, 6}, {1, 4}, {3, 6}, {2, 4}, {3, 5}, {3, 4}};
+
+// Sort `M` (value,pos) pairs descending with the reference's network, return the
+// reference's ret and score (prefix sums in fp32, total in double).
+__device__ inline void net_sort_score(float *val, float *pos, int M, long long *ret, float *score) {
+  const int nex = M == 4 ? 5 : 19;
+  for (int e = 0; e < nex; ++e) {
+    const int a = M == 4 ? kNet4[e][0] : kNet8[e][0];
+    const int b = M == 4 ? kNet4[e][1] : kNet8[e][1];
+    if (val[b] > val[a]) {
+      float t = val[a]; val[a] = val[b]; val[b] = t;
+      t = pos[a]; pos[a] = pos[b]; pos[b] = t;
+    }
+  }
+  *ret = (long long)pos[0];
+  for (int k = 1; k < M; ++k) val[k] = __fadd_rn(val[k], val[k - 1]);
+  double acc = 0.0;
+  for (int k = 0; k < M; ++k) acc += (double)val[k];
+  *score = (float)acc;
+}
+
+struct ExtractEpi {
+  const ExtractParams &P;
+  float m[kP], mL[kP], thr[kP], S[kP], sx[kP], sy[kP], vmid[kP];
+  int idx[kP];
+  int cnt[kP];
+  float *cv;
+  int *ck;
+
+  __device__ explicit ExtractEpi(const ExtractParams &p) : P(p) {
+    const size_t base = ((size_t)blockIdx.x * kThreads + threadIdx.x) * kP * kNC;
+    cv = p.cand_v + base;
+    ck = p.cand_k + base;
+  }
+
+  __device__ __forceinline__ void tile_begin(int, int, int) {
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      m[p] = __int_as_float(0x7f800000);
+      mL[p] = m[p];
+      thr[p] = m[p];
+      S[p] = sx[p] = sy[p] = 0.0f;
+      vmid[p] = 0.0f;
+      idx[p] = 1;
+      cnt[p] = 0;
+    }
+  }
+
+  // keep the kNC smallest values seen, in scan order
+  __device__ __noinline__ static float cand_insert(float *cv, int *ck, int *cnt, float v, int k) {
+    int n = *cnt;
+    if (n == kNC) {
+      int jmax = 0;
+      float vmax = cv[0];
+      for (int j = 1; j < kNC; ++j)
+        if (cv[j] >= vmax) {  // >= : among equals evict the latest
+          vmax = cv[j];
+          jmax = j;
+        }
+      if (!(v < vmax)) return vmax;
+      for (int j = jmax; j + 1 < kNC; ++j) {
+        cv[j] = cv[j + 1];
+        ck[j] = ck[j + 1];
+      }
+      n = kNC - 1;
+    }
+    cv[n] = v;
+    ck[n] = k;
+    *cnt = ++n;
+    if (n < kNC) return __int_as_float(0x7f800000);
+    float vmax = cv[0];
+    for (int j = 1; j < kNC; ++j) vmax = fmaxf(vmax, cv[j]);
+    return vmax;
+  }
+
+  template <int R>
+  __device__ __forceinline__ void block(float (&acc)[kP][R], int dy, int dxb, int rvalid) {
+    const float inf = __int_as_float(0x7f800000);
+    if (rvalid < R) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r >= rvalid) acc[p][r] = inf;
+    }
+    // zero-flow entry, for the tie rule (warp-uniform branch)
+    if (dy == P.mid_dy && P.mid_dx >= dxb && P.mid_dx < dxb + R) {
+      const int rr = P.mid_dx - dxb;
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r == rr) vmid[p] = acc[p][r];
+    }
+    const int kbase = dy * P.g.maxw + dxb + 1;  // 1-based index of r = 0
+    const float rowf = (float)(dy + 1), colf = (float)dxb;
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      float bm = acc[p][0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) bm = fminf(bm, acc[p][r]);
+      if (bm < thr[p]) {
+        // rare path: a new minimum and/or a candidate for the thresholded extraction
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float v = acc[p][r];
+          const bool cand = P.cand_margin > 0.0f;
+          if (v < m[p]) {
+            const float sc = ex2_approx((v - m[p]) * kLog2e);  // m = +inf -> 0
+            S[p] *= sc;
+            sx[p] *= sc;
+            sy[p] *= sc;
+            m[p] = v;
+            mL[p] = v * kLog2e;
+            idx[p] = kbase + r;
+            // invariant: thr = min(m + margin, largest kept candidate) >= m
+            thr[p] = cand ? fminf(thr[p], v + P.cand_margin) : v;
+          }
+          if (cand && v < thr[p]) {
+            const float lmax = cand_insert(cv + p * kNC, ck + p * kNC, &cnt[p], v, kbase + r);
+            thr[p] = fminf(m[p] + P.cand_margin, lmax);
+          }
+        }
+      }
+      float eb = 0.0f, ex = 0.0f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float e = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p]));
+        eb += e;
+        ex = fmaf(e, (float)(r + 1), ex);
+      }
+      S[p] += eb;
+      sx[p] += fmaf(eb, colf, ex);
+      sy[p] = fmaf(eb, rowf, sy[p]);
+    }
+  }
+
+  __device__ __forceinline__ void tile_end(int n, int y, int x0) {
+    const SweepGeom &g = P.g;
+    if (y >= g.H1) return;
+    unsigned untouched = 0;
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const int x = x0 + p;
+      if (x >= g.W1) continue;
+      const size_t o = ((size_t)n * g.H1 + y) * g.W1 + x;
+      const float inv = 1.0f / S[p];
+      int win = idx[p];
+      if ((P.flags & DM_FLAG_TIE_MIDDLE) && win != P.middle) {
+        const float emid = expf(m[p] - vmid[p]);
+        if (emid * inv == inv) win = P.middle;  // p[middle] == max p (opticalflow_model.lua:157-159)
+      }
+      if (P.index) P.index[o] = win;
+      if (P.min_ssd) P.min_ssd[o] = m[p];
+      if (P.pmax) P.pmax[o] = inv;
+      if (P.soft_yx) {
+        const size_t plane = (size_t)g.H1 * g.W1;
+        const size_t so = (size_t)n * 2 * plane + (size_t)y * g.W1 + x;
+        P.soft_yx[so] = sy[p] * inv;
+        P.soft_yx[so + plane] = sx[p] * inv;
+      }
+      if (P.flow_full) {
+        const int row = (win - 1) / g.maxw + 1, col = (win - 1) % g.maxw + 1;
+        const size_t plane = (size_t)P.h_img * P.w_img;
+        const size_t fo = (size_t)n * 2 * plane + (size_t)(y + P.hoff) * P.w_img + (x + P.woff);
+        P.flow_full[fo] = (float)(row - P.cy);
+        P.flow_full[fo + plane] = (float)(col - P.cx);
+      }
+      if (P.index_thr || P.score_thr || P.n_untouched) {
+        float val[8], pos[8];
+        for (int j = 0; j < 8; ++j) val[j] = pos[j] = 0.0f;
+        int got = 0;
+        for (int j = 0; j < cnt[p] && got < P.M; ++j) {
+          const float pk = expf(m[p] - cv[p * kNC + j]) * inv;
+          if ((double)pk > P.thr) {
+            val[got] = pk;
+            pos[got] = (float)ck[p * kNC + j];
+            ++got;
+          }
+        }
+        long long ret = 0;
+        float score = 0.0f;
+        if (got > 0)
+          net_sort_score(val, pos, P.M, &ret, &score);
+        else
+          ++untouched;
+        if (P.index_thr) P.index_thr[o] = ret;
+        if (P.score_thr) P.score_thr[o] = score;
+      }
+    }
+    if (P.n_untouched && untouched) atomicAdd(P.n_untouched + n, (unsigned long long)untouched);
+  }
+};
+
+template <int CT, bool EXACT>
+__global__ void __launch_bounds__(kThreads, 1)
+match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const ExtractParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *ring = reinterpret_cast<float *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kNSlot * P.g.C * P.g.WB);
+  ExtractEpi epi(P);
+  run_sweep<CT, EXACT>(&tmap, P.g, ring, full, epi);
+}
+
+// ---------------------------------------------------------------- volume epilogue
+struct VolumeParams {
+  SweepGeom g;
+  int mode;            // dm_volume_mode
+  const float *vmin;   // [N][H1][W1], mode NEG_SOFTMAX: min_k v_k
+  const float *vinv;   // [N][H1][W1] 1 / sum_k exp(min - v_k)
+  float *out;          // [N][H1][W1][K]
+};
+
+constexpr int kStgStride = kTW + 4;  // floats per staged displacement row (bank-conflict-free)
+
+struct VolumeEpi {
+  const VolumeParams &P;
+  float *stg;  // this warp's staging area: [kRT][kStgStride]
+  float mL[kP], inv[kP];
+  size_t obase;  // output offset of (n, y, tile x)
+  int npx;       // valid pixels of this warp's row in the tile
+  bool rowok;
+
+  __device__ VolumeEpi(const VolumeParams &p, float *stg_all)
+      : P(p), stg(stg_all + (threadIdx.x >> 5) * (kRT * kStgStride)) {}
+
+  __device__ __forceinline__ void tile_begin(int n, int y, int x0) {
+    const SweepGeom &g = P.g;
+    const int lane = threadIdx.x & 31;
+    const int xt = x0 - lane * kP;
+    rowok = y < g.H1;
+    npx = rowok ? min(kTW, g.W1 - xt) : 0;
+    obase = (((size_t)n * g.H1 + (rowok ? y : 0)) * g.W1 + xt) * (size_t)(g.maxh * g.maxw);
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      mL[p] = 0.0f;
+      inv[p] = 1.0f;
+      if (P.mode == DM_VOLUME_NEG_SOFTMAX && rowok && x0 + p < g.W1) {
+        const size_t o = ((size_t)n * g.H1 + y) * g.W1 + x0 + p;
+        mL[p] = P.vmin[o] * kLog2e;
+        inv[p] = P.vinv[o];
+      }
+    }
+  }
+
+  template <int R>
+  __device__ __forceinline__ void block(float (&acc)[kP][R], int dy, int dxb, int rvalid) {
+    const int lane = threadIdx.x & 31;
+    const int K = P.g.maxh * P.g.maxw;
+    if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          acc[p][r] = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p])) * inv[p];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      *reinterpret_cast<float4 *>(stg + r * kStgStride + lane * kP) =
+          make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
+    __syncwarp();
+    // each pixel owns `rvalid` consecutive floats of the output for this (dy, dx-block)
+    const int total = npx * rvalid;
+    float *dst = P.out + obase + (size_t)dy * P.g.maxw + dxb;
+    for (int i = lane; i < total; i += 32) {
+      const int px = i / rvalid, r = i - px * rvalid;
+      dst[(size_t)px * K + r] = stg[r * kStgStride + px];
+    }
+  }
+
+  __device__ __forceinline__ void tile_end(int, int, int) {}
+};
+
+template <int CT, bool EXACT>
+__global__ void __launch_bounds__(kThreads, 1)
+match_volume_kernel(const __grid_constant__ CUtensorMap tmap, const VolumeParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *ring = reinterpret_cast<float *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kNSlot * P.g.C * P.g.WB);
+  float *stg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
+  VolumeEpi epi(P, stg);
+  run_sweep<CT, EXACT>(&tmap, P.g, ring, full, epi);
+}
+
+// ---------------------------------------------------------------- host side
+static size_t ring_bytes(int C, int WB) { return (size_t)kNSlot * C * WB * sizeof(float); }
+
+struct Prepared {
+  SweepGeom g;
+  CUtensorMap tmap;
+  int CT;
+  const float *in1_dev;
+  const float *in2_dev;
+};
+
+// Stage inputs (host -> device, or repack device views TMA cannot describe) and
+// build the tensor map of frame 2: dims {W2, H2, C, N}, box {WB, 1, CT, 1}.  The
+// channel dim of the box is CT >= C: TMA zero-fills the missing channels and the
+// kernel keeps a = 0 for them, so they add exactly 0 to every SSD.
+static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, Prepared *out) {
+  dm_ctx *ctx = call.ctx;
+  DM_REQUIRE(in && in->in1 && in->in2, "input pointers are NULL");
+  DM_REQUIRE(in->n_pairs >= 1 && in->channels >= 1, "n_pairs and channels must be >= 1");
+  DM_REQUIRE(maxh >= 1 && maxw >= 1, "window must be at least 1x1 (got %dx%d)", maxh, maxw);
+  DM_REQUIRE(in->h1 >= 1 && in->w1 >= 1, "empty frame-1 map (%dx%d)", in->h1, in->w1);
+  DM_REQUIRE(in->h2 >= in->h1 + maxh - 1 && in->w2 >= in->w1 + maxw - 1,
+             "frame 2 (%dx%d) smaller than frame 1 (%dx%d) + window (%dx%d) - 1", in->h2, in->w2,
+             in->h1, in->w1, maxh, maxw);
+  SweepGeom &g = out->g;
+  g.N = in->n_pairs;
+  g.C = in->channels;
+  g.Cin = in->channels;
+  g.H1 = in->h1;
+  g.W1 = in->w1;
+  g.H2 = in->h2;
+  g.W2 = in->w2;
+  g.maxh = maxh;
+  g.maxw = maxw;
+  block_schedule(maxw, &g.nfull, &g.tailw);
+  g.WB = slab_width(maxw);
+  g.tiles_x = (g.W1 + kTW - 1) / kTW;
+  g.tiles_y = (g.H1 + kTH - 1) / kTH;
+  g.ntiles = g.tiles_x * g.tiles_y * g.N;
+  out->CT = g.C <= 4 ? 4 : (g.C <= 10 ? 10 : 16);
+
+  long long s1y = in->in1_stride_y ? in->in1_stride_y : g.W1;
+  long long s1c = in->in1_stride_c ? in->in1_stride_c : (long long)g.H1 * s1y;
+  long long s1n = in->in1_stride_n ? in->in1_stride_n : (long long)g.C * s1c;
+  long long s2y = in->in2_stride_y ? in->in2_stride_y : g.W2;
+  long long s2c = in->in2_stride_c ? in->in2_stride_c : (long long)g.H2 * s2y;
+  long long s2n = in->in2_stride_n ? in->in2_stride_n : (long long)g.C * s2c;
+
+  // frame 1: any strides work for the kernel; host data is copied as the smallest
+  // enclosing span of the view.
+  const float *d1 = in->in1;
+  if (classify(in->in1) == PtrKind::Host) {
+    const size_t span = (size_t)((g.N - 1) * s1n + (g.C - 1) * s1c + (g.H1 - 1) * s1y + g.W1);
+    const void *p = nullptr;
+    DM_CHECK(call.in(in->in1, span * sizeof(float), &p));
+    d1 = static_cast<const float *>(p);
+  }
+  g.in1 = d1;
+  g.s1n = s1n;
+  g.s1c = s1c;
+  g.s1y = s1y;
+
+  // frame 2: TMA needs a 16-byte aligned base and 16-byte multiple strides.
+  const float *d2 = in->in2;
+  const bool host2 = classify(in->in2) == PtrKind::Host;
+  const bool tma_ok = ((uintptr_t)in->in2 % 16 == 0) && (s2y % 4 == 0) && (s2c % 4 == 0) &&
+                      (s2n % 4 == 0);
+  const bool dense2 = s2y == g.W2 && s2c == (long long)g.H2 * g.W2 && s2n == (long long)g.C * s2c;
+  if (host2 && dense2 && g.W2 % 4 == 0) {
+    const void *p = nullptr;
+    DM_CHECK(call.in(in->in2, (size_t)g.N * s2n * sizeof(float), &p));
+    d2 = static_cast<const float *>(p);
+  } else if (host2 || !tma_ok) {
+    const long long py = (g.W2 + 3) & ~3LL;  // padded pitch
+    void *buf = nullptr;
+    DM_CHECK(call.alloc(&buf, (size_t)g.N * g.C * g.H2 * py * sizeof(float)));
+    // one pitched copy per (n, c) plane keeps arbitrary strides simple
+    for (int n = 0; n < g.N; ++n)
+      for (int c = 0; c < g.C; ++c) {
+        const float *src = in->in2 + n * s2n + c * s2c;
+        float *dst = static_cast<float *>(buf) + ((size_t)n * g.C + c) * g.H2 * py;
+        DM_CUDA(cudaMemcpy2DAsync(dst, py * sizeof(float), src, s2y * sizeof(float),
+                                  g.W2 * sizeof(float), g.H2,
+                                  host2 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+      }
+    if (host2) ctx->call_has_host = true;
+    d2 = static_cast<const float *>(buf);
+    s2y = py;
+    s2c = (long long)g.H2 * py;
+    s2n = (long long)g.C * s2c;
+  }
+  out->in1_dev = d1;
+  out->in2_dev = d2;
+  const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, (uint64_t)g.C, (uint64_t)g.N};
+  const uint64_t strides[3] = {(uint64_t)s2y * 4, (uint64_t)s2c * 4, (uint64_t)s2n * 4};
+  const uint32_t box[4] = {(uint32_t)g.WB, 1u, (uint32_t)out->CT, 1u};
+  DM_CHECK(encode_tensor_map_4d(&out->tmap, d2, dims, strides, box));
+  // the kernels address the ring with the box's channel count
+  g.C = out->CT;
+  return DM_OK;
+}
+
+int generic_match_extract(Call &call, const dm_pair *in, int maxh, int maxw, unsigned flags,
+                          double thr, int h_img, int w_img, const dm_extract_out *out);
+int generic_match_volume(Call &call, const dm_pair *in, int maxh, int maxw, int mode, bool exact,
+                         float *out);
+
+static int grid_for(dm_ctx *ctx, const void *kernel, size_t smem, int ntiles) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  if (per_sm < 1) per_sm = 1;
+  const int cap = ctx->num_sms * per_sm;
+  return ntiles < cap ? ntiles : cap;
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, unsigned flags,
+                                double prob_threshold, int h_img, int w_img,
+                                const dm_extract_out *out) {
+  DM_REQUIRE(ctx && in && out, "dm_match_extract: NULL argument");
+  DM_CUDA(cudaSetDevice(ctx->device));
+  const bool want_thr = out->index_thr || out->score_thr || out->n_untouched;
+  DM_REQUIRE(!want_thr || (prob_threshold > 0.1 && prob_threshold < 1.0),
+             "dm_match_extract: fused thresholded extraction needs 0.1 < prob_threshold < 1 "
+             "(got %g); use dm_match_volume + dm_extract_output for other thresholds",
+             prob_threshold);
+  if (out->flow_full)
+    DM_REQUIRE(h_img >= in->h1 && w_img >= in->w1, "canvas %dx%d smaller than output %dx%d", h_img,
+               w_img, in->h1, in->w1);
+  Call call(ctx);
+  if (in->channels > kMaxC) {
+    int rc = generic_match_extract(call, in, maxh, maxw, flags, prob_threshold, h_img, w_img, out);
+    int rf = call.finish();
+    return rc != DM_OK ? rc : rf;
+  }
+  Prepared pr;
+  DM_CHECK(prepare(call, in, maxh, maxw, &pr));
+  const SweepGeom &g = pr.g;
+  const size_t npx = (size_t)g.N * g.H1 * g.W1;
+
+  ExtractParams P;
+  P.g = g;
+  P.flags = flags;
+  P.thr = prob_threshold;
+  // v_k < min + ln(1/thr) is necessary for p_k > thr; <= 0 switches candidates off
+  P.cand_margin = want_thr ? (float)(log(1.0 / prob_threshold) + 1e-3) : 0.0f;
+  P.M = prob_threshold < 0.2 ? 8 : 4;
+  P.cy = (maxh + 1) / 2;
+  P.cx = (maxw + 1) / 2;
+  P.mid_dy = P.cy - 1;
+  P.mid_dx = P.cx - 1;
+  P.middle = P.mid_dy * maxw + P.mid_dx + 1;
+  P.h_img = h_img;
+  P.w_img = w_img;
+  P.hoff = (h_img - g.H1) / 2;
+  P.woff = (w_img - g.W1) / 2;
+
+  void *p;
+#define DM_OUT(field, type, bytes)                                \
+  P.field = nullptr;                                              \
+  if (out->field) {                                               \
+    DM_CHECK(call.out(out->field, (bytes), &p));                  \
+    P.field = static_cast<type *>(p);                             \
+  }
+  DM_OUT(index, long long, npx * 8)
+  DM_OUT(min_ssd, float, npx * 4)
+  DM_OUT(pmax, float, npx * 4)
+  DM_OUT(flow_full, float, (size_t)g.N * 2 * h_img * w_img * 4)
+  DM_OUT(index_thr, long long, npx * 8)
+  DM_OUT(score_thr, float, npx * 4)
+  DM_OUT(soft_yx, float, npx * 2 * 4)
+#undef DM_OUT
+  P.n_untouched = nullptr;
+  if (out->n_untouched) {
+    DM_CHECK(call.out(out->n_untouched, (size_t)g.N * 8, &p));
+    P.n_untouched = static_cast<unsigned long long *>(p);
+    DM_CUDA(cudaMemsetAsync(p, 0, (size_t)g.N * 8, ctx->stream));
+  }
+  if (P.flow_full)
+    DM_CUDA(cudaMemsetAsync(P.flow_full, 0, (size_t)g.N * 2 * h_img * w_img * 4, ctx->stream));
+
+  const size_t smem = ring_bytes(g.C, g.WB) + kBarBytes;
+  DM_REQUIRE(smem <= ctx->smem_optin, "window %dx%d with %d channels needs %zu bytes of shared memory",
+             maxh, maxw, g.C, smem);
+  const bool exact = flags & DM_FLAG_EXACT_SSD;
+  const void *kfn = nullptr;
+#define DM_PICK(ct)                                                                   \
+  (exact ? (const void *)match_extract_kernel<ct, true> : (const void *)match_extract_kernel<ct, false>)
+  kfn = pr.CT == 4 ? DM_PICK(4) : (pr.CT == 10 ? DM_PICK(10) : DM_PICK(16));
+#undef DM_PICK
+  DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = grid_for(ctx, kfn, smem, g.ntiles);
+  void *scratch = nullptr;
+  DM_CHECK(call.alloc(&scratch, (size_t)grid * kThreads * kP * kNC * 8));
+  P.cand_v = static_cast<float *>(scratch);
+  P.cand_k = reinterpret_cast<int *>(P.cand_v + (size_t)grid * kThreads * kP * kNC);
+  void *args[] = {(void *)&pr.tmap, (void *)&P};
+  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+  count_launch(ctx);
+  return call.finish();
+}
+
+// ---------------------------------------------------------------- volume API
+namespace dm {
+
+// statistics pass for the soft-max volume: per-pixel min and 1/sum, nothing else
+static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin, float *vinv) {
+  dm_ctx *ctx = call.ctx;
+  const SweepGeom &g = pr.g;
+  ExtractParams P;
+  memset(&P, 0, sizeof(P));
+  P.g = g;
+  P.flags = 0;
+  P.thr = 1.0;
+  P.cand_margin = 0.0f;
+  P.M = 8;
+  P.cy = (g.maxh + 1) / 2;
+  P.cx = (g.maxw + 1) / 2;
+  P.mid_dy = P.cy - 1;
+  P.mid_dx = P.cx - 1;
+  P.middle = P.mid_dy * g.maxw + P.mid_dx + 1;
+  P.min_ssd = vmin;
+  P.pmax = vinv;
+  const size_t smem = ring_bytes(g.C, g.WB) + kBarBytes;
+  const void *kfn;
+#define DM_PICK(ct)                                                                   \
+  (exact ? (const void *)match_extract_kernel<ct, true> : (const void *)match_extract_kernel<ct, false>)
+  kfn = pr.CT == 4 ? DM_PICK(4) : (pr.CT == 10 ? DM_PICK(10) : DM_PICK(16));
+#undef DM_PICK
+  DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = grid_for(ctx, kfn, smem, g.ntiles);
+  void *scratch = nullptr;
+  DM_CHECK(call.alloc(&scratch, (size_t)grid * kThreads * kP * kNC * 8));
+  P.cand_v = static_cast<float *>(scratch);
+  P.cand_k = reinterpret_cast<int *>(P.cand_v + (size_t)grid * kThreads * kP * kNC);
+  void *args[] = {(void *)&pr.tmap, (void *)&P};
+  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+  count_launch(ctx);
+  return DM_OK;
+}
+
+}  // namespace dm
+
+extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, int mode,
+                               float *out) {
+  DM_REQUIRE(ctx && in && out, "dm_match_volume: NULL argument");
+  const bool exact = (mode & DM_VOLUME_EXACT) != 0;
+  mode &= ~DM_VOLUME_EXACT;
+  DM_REQUIRE(mode == DM_VOLUME_SSD || mode == DM_VOLUME_NEG_SOFTMAX, "dm_match_volume: bad mode %d",
+             mode);
+  DM_CUDA(cudaSetDevice(ctx->device));
+  Call call(ctx);
+  if (in->channels > kMaxC) {
+    int rc = generic_match_volume(call, in, maxh, maxw, mode, exact, out);
+    int rf = call.finish();
+    return rc != DM_OK ? rc : rf;
+  }
+  Prepared pr;
+  DM_CHECK(prepare(call, in, maxh, maxw, &pr));
+  const SweepGeom &g = pr.g;
+  const size_t npx = (size_t)g.N * g.H1 * g.W1;
+  const size_t K = (size_t)maxh * maxw;
+  void *p = nullptr;
+  DM_CHECK(call.out(out, npx * K * sizeof(float), &p));
+  VolumeParams P;
+  P.g = g;
+  P.mode = mode;
+  P.vmin = P.vinv = nullptr;
+  P.out = static_cast<float *>(p);
+  if (mode == DM_VOLUME_NEG_SOFTMAX) {
+    void *s = nullptr;
+    DM_CHECK(call.alloc(&s, npx * 2 * sizeof(float)));
+    float *vmin = static_cast<float *>(s), *vinv = vmin + npx;
+    DM_CHECK(launch_stats(call, pr, exact, vmin, vinv));
+    P.vmin = vmin;
+    P.vinv = vinv;
+  }
+  const size_t smem = ring_bytes(g.C, g.WB) + kBarBytes +
+                      (size_t)kWarps * kRT * kStgStride * sizeof(float);
+  DM_REQUIRE(smem <= ctx->smem_optin, "window %dx%d with %d channels needs %zu bytes of shared memory",
+             maxh, maxw, g.C, smem);
+#define DM_PICKV(ct)                                                                  \
+  (exact ? (const void *)match_volume_kernel<ct, true> : (const void *)match_volume_kernel<ct, false>)
+  const void *kfn = pr.CT == 4 ? DM_PICKV(4) : (pr.CT == 10 ? DM_PICKV(10) : DM_PICKV(16));
+#undef DM_PICKV
+  DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = grid_for(ctx, kfn, smem, g.ntiles);
+  void *args[] = {(void *)&pr.tmap, (void *)&P};
+  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+  count_launch(ctx);
+  return call.finish();
+}

@@ -1,0 +1,855 @@
+"""Host-side mirror of the reference's Lua surface (see package docstring).
+
+Arrays may be numpy arrays (host memory: staged by the library, call complete at
+return) or torch CUDA tensors (device pointers: enqueued on torch's current
+stream).  Outputs follow the inputs' kind.  Index conventions are the
+reference's (1-based window indices, LongTensor = int64).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import (DM_FLAG_EXACT_SSD, DM_FLAG_TIE_MIDDLE, DM_VOLUME_EXACT, DM_VOLUME_NEG_SOFTMAX,
+                   DM_VOLUME_SSD, DepthMatchError, check, dm_extract_out, dm_pair)
+
+__all__ = [
+    "Context", "default_context", "Geometry", "nn", "extractoutput", "yx2x", "x2yx",
+    "centered2onebased", "onebased2centered", "getMiddleIndex", "prepareInput", "getModel",
+    "DenseMatch", "processOutput", "getOutputConfidences", "getOutputConfidences2", "yx2xMulti",
+    "x2yxMulti", "x2yxMulti2", "x2yxMultiNumber", "getModelMultiscale", "multiscaleLength",
+    "getRMax", "getC2PMask", "getP2CMask", "cartesian2polar", "polar2cartesian", "getKOutput",
+    "getP2CMaskOF", "flow2depth", "match_extract", "match_volume", "round_lua",
+]
+
+try:  # torch is plumbing only (device memory + streams); the package works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+# ------------------------------------------------------------------ context
+class Context:
+    """One dm_ctx: a device, a stream, a workspace.  One per GPU per thread."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.dm_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._stream = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        check(self._lib.dm_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self._lib.dm_launch_count(self._h))
+
+    def use_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        if cuda_stream != self._stream:
+            check(self._lib.dm_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+            self._stream = cuda_stream
+
+
+_default = {}
+
+
+def default_context(device=0):
+    ctx = _default.get(device)
+    if ctx is None:
+        ctx = _default[device] = Context(device)
+    return ctx
+
+
+class _Args:
+    """Collects pointers for one library call and remembers what must stay alive."""
+
+    def __init__(self, ctx=None):
+        self.keep = []
+        self.on_device = False
+        self.ctx = ctx
+
+    def inp(self, x, dtype=np.float32):
+        if _is_torch(x):
+            tdt = {np.float32: torch.float32, np.int64: torch.int64}[dtype]
+            if x.dtype != tdt or not x.is_contiguous():
+                x = x.to(tdt).contiguous()
+            self.keep.append(x)
+            if x.is_cuda:
+                self.on_device = True
+                return x.data_ptr(), x
+            return x.data_ptr(), x
+        a = np.ascontiguousarray(x, dtype=dtype)
+        self.keep.append(a)
+        return a.ctypes.data, a
+
+    def out(self, shape, dtype=np.float32, like=None, device_index=0):
+        if like is not None and _is_torch(like) and like.is_cuda:
+            tdt = {np.float32: torch.float32, np.int64: torch.int64}[dtype]
+            t = torch.empty(tuple(int(s) for s in shape), dtype=tdt, device=like.device)
+            self.keep.append(t)
+            self.on_device = True
+            return t.data_ptr(), t
+        a = np.empty(tuple(int(s) for s in shape), dtype=dtype)
+        self.keep.append(a)
+        return a.ctypes.data, a
+
+    def ctx_for(self, *tensors):
+        cuda = [t for t in tensors if _is_torch(t) and t.is_cuda]
+        if self.ctx is not None:
+            ctx = self.ctx
+        else:
+            ctx = default_context((cuda[0].device.index or 0) if cuda else 0)
+        if cuda:  # order the library's work after torch's on the tensors' stream
+            ctx.use_stream(torch.cuda.current_stream(cuda[0].device).cuda_stream)
+        return ctx
+
+
+def _pair_struct(args, in1, in2):
+    """in1: [N,]C,H1,W1 (may be a strided view with unit innermost stride), in2: [N,]C,H2,W2."""
+    def strides_of(x):
+        if _is_torch(x):
+            return [int(s) for s in x.stride()], x.data_ptr()
+        return [int(s // x.itemsize) for s in x.strides], x.ctypes.data
+
+    def prep(x):
+        if _is_torch(x):
+            if x.dtype != torch.float32:
+                x = x.float()
+            if x.dim() == 3:
+                x = x.unsqueeze(0)
+            if x.stride(-1) != 1 or any(s < 0 for s in x.stride()):
+                x = x.contiguous()
+            if x.is_cuda:
+                args.on_device = True
+        else:
+            x = np.asarray(x)
+            if x.dtype != np.float32:
+                x = x.astype(np.float32)
+            if x.ndim == 3:
+                x = x[None]
+            if x.strides[-1] != x.itemsize or any(s < 0 for s in x.strides):
+                x = np.ascontiguousarray(x)
+        args.keep.append(x)
+        return x
+
+    a, b = prep(in1), prep(in2)
+    if a.ndim != 4 or b.ndim != 4:
+        raise DepthMatchError(_lib.DM_ERR_INVALID, "inputs must be [N,]C,H,W")
+    if tuple(a.shape[:2]) != tuple(b.shape[:2]):
+        raise DepthMatchError(_lib.DM_ERR_INVALID, "in1 and in2 differ in pairs/channels")
+    sa, pa = strides_of(a)
+    sb, pb = strides_of(b)
+    p = dm_pair()
+    p.in1, p.in2 = pa, pb
+    p.n_pairs, p.channels = int(a.shape[0]), int(a.shape[1])
+    p.h1, p.w1, p.h2, p.w2 = int(a.shape[2]), int(a.shape[3]), int(b.shape[2]), int(b.shape[3])
+    p.in1_stride_n, p.in1_stride_c, p.in1_stride_y = sa[0] or 1, sa[1], sa[2]
+    p.in2_stride_n, p.in2_stride_c, p.in2_stride_y = sb[0] or 1, sb[1], sb[2]
+    return p, a, b
+
+
+# --------------------------------------------------------- low-level wrappers
+def match_volume(in1, in2, maxh, maxw, softmax=False, exact=False, ctx=None):
+    """nn.SpatialMatching (+ Minus + SoftMax when softmax=True): [N,]H1,W1,maxh,maxw."""
+    args = _Args(ctx)
+    single = (in1.dim() if _is_torch(in1) else np.ndim(in1)) == 3
+    p, a, b = _pair_struct(args, in1, in2)
+    c = args.ctx_for(a, b)
+    optr, out = args.out((p.n_pairs, p.h1, p.w1, maxh, maxw), np.float32, like=a)
+    mode = (DM_VOLUME_NEG_SOFTMAX if softmax else DM_VOLUME_SSD) | (DM_VOLUME_EXACT if exact else 0)
+    check(c._lib.dm_match_volume(c.handle, C.byref(p), maxh, maxw, mode, optr))
+    return out[0] if single else out
+
+
+def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_threshold=0.11,
+                  canvas=None, want=("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx"),
+                  ctx=None):
+    """Fused prepareInput-less forward + processOutput.  Returns a dict of arrays, each
+    [N,]H1,W1 (soft_yx: [N,]2,H1,W1; flow_full: [N,]2,hImg,wImg when canvas=(hImg,wImg))."""
+    args = _Args(ctx)
+    single = (in1.dim() if _is_torch(in1) else np.ndim(in1)) == 3
+    p, a, b = _pair_struct(args, in1, in2)
+    c = args.ctx_for(a, b)
+    N, H1, W1 = p.n_pairs, p.h1, p.w1
+    o = dm_extract_out()
+    res = {}
+    shapes = {"index": ((N, H1, W1), np.int64), "min_ssd": ((N, H1, W1), np.float32),
+              "pmax": ((N, H1, W1), np.float32), "index_thr": ((N, H1, W1), np.int64),
+              "score_thr": ((N, H1, W1), np.float32), "soft_yx": ((N, 2, H1, W1), np.float32),
+              "n_untouched": ((N,), np.int64)}
+    want = list(want)
+    if canvas is not None and "flow_full" not in want:
+        want.append("flow_full")
+    for name in want:
+        if name == "flow_full":
+            if canvas is None:
+                raise DepthMatchError(_lib.DM_ERR_INVALID, "flow_full needs canvas=(hImg, wImg)")
+            shape, dt = (N, 2, int(canvas[0]), int(canvas[1])), np.float32
+        else:
+            shape, dt = shapes[name]
+        ptr, arr = args.out(shape, dt, like=a)
+        setattr(o, name, ptr)
+        res[name] = arr
+    flags = (DM_FLAG_TIE_MIDDLE if tie_middle else 0) | (DM_FLAG_EXACT_SSD if exact else 0)
+    himg, wimg = (int(canvas[0]), int(canvas[1])) if canvas is not None else (H1, W1)
+    check(c._lib.dm_match_extract(c.handle, C.byref(p), maxh, maxw, flags, float(prob_threshold),
+                                  himg, wimg, C.byref(o)))
+    if single:
+        res = {k: v[0] for k, v in res.items()}
+    return res
+
+
+# ------------------------------------------------------------------ geometry
+class Geometry(dict):
+    """The reference's `geometry` table (opticalflow.lua:138-198): attribute access."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            return None
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def round_lua(x):
+    """common.lua round(): floor(x + 0.5)."""
+    return math.floor(x + 0.5)
+
+
+# opticalflow_model.lua:12-43
+def yx2x(geometry, y, x):
+    return (y - 1) * geometry.maxw + x
+
+
+def x2yx(geometry, x):
+    if isinstance(x, (int, float)):
+        return math.floor((x - 1) / geometry.maxw) + 1, (x - 1) % geometry.maxw + 1
+    xd = (x.double() if _is_torch(x) else np.asarray(x, np.float64)) - 1
+    yout = (xd / geometry.maxw).floor() if _is_torch(x) else np.floor(xd / geometry.maxw)
+    xout = xd - yout * geometry.maxw
+    if _is_torch(x):
+        return (yout + 1.5).floor(), (xout + 1.5).floor()
+    return np.floor(yout + 1.5), np.floor(xout + 1.5)
+
+
+def centered2onebased(geometry, y, x):
+    return y + math.ceil(geometry.maxh / 2), x + math.ceil(geometry.maxw / 2)
+
+
+def onebased2centered(geometry, y, x):
+    return y - math.ceil(geometry.maxh / 2), x - math.ceil(geometry.maxw / 2)
+
+
+def getMiddleIndex(geometry):
+    if geometry.multiscale:
+        return yx2xMulti(geometry, 0, 0)
+    y, x = centered2onebased(geometry, 0, 0)
+    return yx2x(geometry, y, x)
+
+
+# opticalflow_model.lua:131-151
+def prepareInput(geometry, patch1, patch2):
+    if tuple(patch1.shape) != tuple(patch2.shape):
+        raise DepthMatchError(_lib.DM_ERR_INVALID, "prepareInput: patches differ in size")
+    if geometry.multiscale:
+        return [patch1, patch2]
+    h, w = patch1.shape[1], patch1.shape[2]
+    oy, ox = math.ceil(geometry.maxh / 2) - 1, math.ceil(geometry.maxw / 2) - 1
+    return [patch1[:, oy:oy + h - geometry.maxh + 1, ox:ox + w - geometry.maxw + 1], patch2]
+
+
+# ------------------------------------------------------------------ nn modules
+class _Module:
+    def forward(self, inp):
+        return self.updateOutput(inp)
+
+    __call__ = forward
+
+    def updateGradInput(self, inp, gradOutput):
+        raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED,
+                              "%s: backward is outside the inference hot path" % type(self).__name__)
+
+    backward = accGradParameters = updateGradInput
+
+    def parameters(self):
+        return [], []
+
+
+class SpatialMatching(_Module):
+    """nn.SpatialMatching(maxh, maxw, full_output) (nnx; opticalflow_model.lua:93)."""
+
+    def __init__(self, maxh, maxw, full_output=False, exact=False, ctx=None):
+        if full_output:
+            raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED, "full_output=true is never used by the reference")
+        self.maxh, self.maxw, self.full_output, self.exact, self.ctx = maxh, maxw, False, exact, ctx
+        self.output = None
+
+    def updateOutput(self, inp):
+        self.output = match_volume(inp[0], inp[1], self.maxh, self.maxw, exact=self.exact, ctx=self.ctx)
+        return self.output
+
+
+class SpatialRadialMatching(_Module):
+    """nn.SpatialRadialMatching(hWin) (radial/radial_opticalflow_network.lua:32-34): H1 x W x hWin."""
+
+    def __init__(self, hWin, ctx=None):
+        self.hWin, self.ctx = hWin, ctx
+        self.output = None
+
+    def updateOutput(self, inp):
+        v = match_volume(inp[0], inp[1], self.hWin, 1, exact=True, ctx=self.ctx)
+        self.output = v.reshape(tuple(v.shape[:-2]) + (self.hWin,))
+        return self.output
+
+    def argmin_flow(self, inp):
+        """matcher + `output:min(3)`, idx-1 (radial/test_radial_opticalflow.lua:204-207), fused."""
+        args = _Args(self.ctx)
+        single = (inp[0].dim() if _is_torch(inp[0]) else np.ndim(inp[0])) == 3
+        p, a, b = _pair_struct(args, inp[0], inp[1])
+        c = args.ctx_for(a, b)
+        fptr, flow = args.out((p.n_pairs, p.h1, p.w1), np.float32, like=a)
+        mptr, mn = args.out((p.n_pairs, p.h1, p.w1), np.float32, like=a)
+        check(c._lib.dm_radial_match_extract(c.handle, C.byref(p), self.hWin, fptr, mptr))
+        return (flow[0], mn[0]) if single else (flow, mn)
+
+
+class CascadingAddTable(_Module):
+    """nn.CascadingAddTable(ratios, trainable, single_beta), forward only (CascadingAddTable.lua)."""
+
+    def __init__(self, ratios, trainable=True, single_beta=False, ctx=None):
+        self.ratios, self.trainable, self.ctx = list(ratios), trainable, ctx
+        self.output = []
+
+    def updateOutput(self, inp):
+        if len(inp) != len(self.ratios):
+            raise DepthMatchError(_lib.DM_ERR_INVALID,
+                                  "nn.CascadingAddTable: input and ratios must have the same size")
+        for t in inp:
+            if len(t.shape) != 3:
+                raise DepthMatchError(_lib.DM_ERR_INVALID, "nn.CascadingAddTable: input must be a "
+                                      "table of 3D-tensors (HxW) x Kh x Kw")
+        args = _Args(self.ctx)
+        if _is_torch(inp[0]):
+            stacked = torch.stack([t.float() for t in inp]).contiguous()
+        else:
+            stacked = np.stack([np.asarray(t, np.float32) for t in inp])
+        iptr, stacked = args.inp(stacked)
+        c = args.ctx_for(stacked)
+        n, rows, kh, kw = stacked.shape
+        optr, out = args.out(stacked.shape, np.float32, like=stacked)
+        rat = (C.c_int * n)(*self.ratios)
+        check(c._lib.dm_cascade_add(c.handle, iptr, rows, kh, kw, rat, n, optr))
+        self.output = [out[i] for i in range(n)]
+        return self.output
+
+
+class OutputExtractor(_Module):
+    """nn.OutputExtractor(maxh, maxw): {x, y} soft means (OutputExtractor.lua:21-35)."""
+
+    def __init__(self, maxh, maxw, ctx=None):
+        self.maxh, self.maxw, self.ctx = maxh, maxw, ctx
+        self.output = None
+
+    def updateOutput(self, inp):
+        args = _Args(self.ctx)
+        iptr, a = args.inp(inp)
+        c = args.ctx_for(a)
+        h, w = a.shape[0], a.shape[1]
+        yptr, y = args.out((h, w), np.float32, like=a)
+        xptr, x = args.out((h, w), np.float32, like=a)
+        check(c._lib.dm_soft_mean(c.handle, iptr, h * w, self.maxh, self.maxw, yptr, xptr))
+        self.output = [x, y]
+        return self.output
+
+
+class _NN:
+    SpatialMatching = SpatialMatching
+    SpatialRadialMatching = SpatialRadialMatching
+    CascadingAddTable = CascadingAddTable
+    OutputExtractor = OutputExtractor
+
+
+nn = _NN()
+
+
+class _ExtractOutput:
+    """`require 'extractoutput'` (extract_output.cpp:357-366): in-place on ret/scores."""
+
+    @staticmethod
+    def extractOutput(inp, scores, threshold, ret, ctx=None):
+        args = _Args(ctx)
+        iptr, a = args.inp(inp)
+        c = args.ctx_for(a)
+        h, w, n = a.shape
+        _check_inplace(scores, np.float32, (h, w))
+        _check_inplace(ret, np.int64, (h, w))
+        nun = C.c_int64(0)
+        check(c._lib.dm_extract_output(c.handle, iptr, h, w, n, float(threshold), _ptr(ret),
+                                       _ptr(scores), C.byref(nun)))
+        return int(nun.value)
+
+    @staticmethod
+    def extractOutputMarginalized(inp, threshold, threshold_acc, ret, retgd, ctx=None):
+        args = _Args(ctx)
+        iptr, a = args.inp(inp)
+        c = args.ctx_for(a)
+        h, w, n = a.shape
+        _check_inplace(ret, np.int64, (h, w))
+        _check_inplace(retgd, np.int64, (h, w))
+        check(c._lib.dm_extract_output_marginalized(c.handle, iptr, h, w, n, float(threshold),
+                                                    float(threshold_acc), _ptr(ret), _ptr(retgd)))
+
+
+extractoutput = _ExtractOutput()
+
+
+def _ptr(x):
+    return x.data_ptr() if _is_torch(x) else x.ctypes.data
+
+
+def _check_inplace(x, dtype, shape):
+    if _is_torch(x):
+        ok = x.is_contiguous() and tuple(x.shape) == tuple(shape) and \
+            x.dtype == {np.float32: torch.float32, np.int64: torch.int64}[dtype]
+    else:
+        ok = isinstance(x, np.ndarray) and x.flags.c_contiguous and x.dtype == dtype and \
+            tuple(x.shape) == tuple(shape)
+    if not ok:
+        raise DepthMatchError(_lib.DM_ERR_INVALID, "output tensor must be contiguous %s of shape %s"
+                              % (np.dtype(dtype).name, tuple(shape)))
+
+
+# ------------------------------------------------------------------ models
+class _MatchModel(_Module):
+    """getModel(geometry, full_image, prefiltered=true) (opticalflow_model.lua:81-129):
+    SpatialMatching -> Minus -> SoftMax [-> OutputExtractor].  forward() returns what the
+    reference's model:forward returns: the H1 x W1 x (maxh*maxw) probability volume."""
+
+    def __init__(self, geometry, ctx=None):
+        self.geometry, self.ctx = geometry, ctx
+        self.output = None
+
+    def updateOutput(self, inp):
+        g = self.geometry
+        v = match_volume(inp[0], inp[1], g.maxh, g.maxw, softmax=True, ctx=self.ctx)
+        v = v.reshape(tuple(v.shape[:-2]) + (g.maxh * g.maxw,))
+        if g.output_extraction_method == "mean":
+            self.output = OutputExtractor(g.maxh, g.maxw, ctx=self.ctx).forward(v)
+        else:
+            self.output = v
+        return self.output
+
+
+class FusedOutput(dict):
+    """What DenseMatch.forward returns: per-pixel results, no volume."""
+
+
+class DenseMatch(_Module):
+    """nn.DenseMatch: the fused replacement for getModel's graph + processOutput's reductions
+    (depth_estimation_api.lua:164-168 become one call)."""
+
+    def __init__(self, geometry, exact=False, ctx=None):
+        self.geometry, self.exact, self.ctx = geometry, exact, ctx
+        self.output = None
+
+    def updateOutput(self, inp):
+        g = self.geometry
+        canvas = (g.hImg, g.wImg) if g.hImg and g.wImg else None
+        self.output = FusedOutput(match_extract(inp[0], inp[1], g.maxh, g.maxw, tie_middle=True,
+                                                exact=self.exact, canvas=canvas, ctx=self.ctx,
+                                                want=("index", "pmax", "index_thr", "score_thr",
+                                                      "soft_yx")))
+        return self.output
+
+
+def getModel(geometry, full_image=True, prefiltered=True, fused=False, ctx=None):
+    if not prefiltered:
+        raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED, "getModel: the conv feature extractor "
+                              "(getFilter) is outside the matching hot path; pass prefiltered maps")
+    if geometry.multiscale:
+        return getModelMultiscale(geometry, full_image, prefiltered, ctx=ctx)
+    return DenseMatch(geometry, ctx=ctx) if fused else _MatchModel(geometry, ctx=ctx)
+
+
+# opticalflow_model.lua:153-169
+def getOutputConfidences(geometry, inp, threshold=None, ctx=None):
+    args = _Args(ctx)
+    iptr, a = args.inp(inp)
+    c = args.ctx_for(a)
+    h, w, K = a.shape
+    if threshold is None:
+        iptr2, idx = args.out((h, w), np.int64, like=a)
+        check(c._lib.dm_argmax_tie(c.handle, iptr, h * w, K, int(getMiddleIndex(geometry)), 0, iptr2,
+                                   None))
+        ones = torch.ones((h, w), device=a.device) if _is_torch(a) else np.ones((h, w), np.float32)
+        return idx, ones
+    # the reference allocates uninitialised tensors here (:163-164); we start from zeros
+    imaxs = torch.zeros((h, w), dtype=torch.int64, device=a.device) if _is_torch(a) else np.zeros((h, w), np.int64)
+    scores = torch.zeros((h, w), device=a.device) if _is_torch(a) else np.zeros((h, w), np.float32)
+    extractoutput.extractOutput(a, scores, 0.11, imaxs, ctx=c)
+    return imaxs, scores > threshold
+
+
+# opticalflow_model.lua:171-199
+def getOutputConfidences2(geometry, inp, ctx=None):
+    x, y = OutputExtractor(geometry.maxh, geometry.maxw, ctx=ctx).forward(inp)
+    args = _Args(ctx)
+    iptr, a = args.inp(inp)
+    c = args.ctx_for(a)
+    h, w, K = a.shape
+    mptr, pm = args.out((h, w, geometry.maxh), np.float32, like=a)
+    check(c._lib.dm_marginal_x(c.handle, iptr, h * w, geometry.maxh, geometry.maxw, mptr))
+    imaxs = torch.zeros((h, w), dtype=torch.int64, device=a.device) if _is_torch(a) else np.zeros((h, w), np.int64)
+    scores = torch.zeros((h, w), device=a.device) if _is_torch(a) else np.zeros((h, w), np.float32)
+    extractoutput.extractOutput(pm, scores, 0.11, imaxs, ctx=c)
+    return y, x, scores > 0
+
+
+# opticalflow_model.lua:201-252
+def processOutput(geometry, output, process_full=None, threshold=None, ctx=None):
+    ret = {}
+    if isinstance(output, MultiscaleOutput):
+        ret["index"], ret["y"], ret["x"] = output["index"], output["flow_y"], output["flow_x"]
+        ret["confidences"] = _ones_like(ret["index"])
+    elif isinstance(output, FusedOutput):
+        yoff, xoff = centered2onebased(geometry, 0, 0)
+        if geometry.output_extraction_method == "mean":
+            ret["y"], ret["x"] = output["soft_yx"][..., 0, :, :] - yoff, output["soft_yx"][..., 1, :, :] - xoff
+            fy = _floor(output["soft_yx"][..., 0, :, :] + 0.5)
+            fx = _floor(output["soft_yx"][..., 1, :, :] + 0.5)
+            ret["index"] = _to_long(yx2x(geometry, fy, fx))
+            ret["confidences"] = _ones_like(ret["index"])
+        else:
+            if threshold is None:
+                ret["index"] = output["index"]
+                ret["confidences"] = _ones_like(ret["index"])
+            else:
+                ret["index"] = output["index_thr"]
+                ret["confidences"] = output["score_thr"] > threshold
+            ry, rx = x2yx(geometry, ret["index"])
+            ret["y"], ret["x"] = ry - yoff, rx - xoff
+    elif geometry.output_extraction_method == "max" or geometry.output_extraction_method is None:
+        ret["index"], ret["confidences"] = getOutputConfidences(geometry, output, threshold, ctx=ctx)
+        if geometry.multiscale:
+            ret["y"], ret["x"] = x2yxMulti(geometry, ret["index"], ctx=ctx)
+        else:
+            ry, rx = x2yx(geometry, ret["index"])
+            yoff, xoff = centered2onebased(geometry, 0, 0)
+            ret["y"], ret["x"] = ry - yoff, rx - xoff
+    else:
+        ret["y"], ret["x"], ret["confidences"] = getOutputConfidences2(geometry, output, ctx=ctx)
+        ret["index"] = _to_long(yx2x(geometry, _floor(ret["y"] + 0.5), _floor(ret["x"] + 0.5)))
+        yoff, xoff = centered2onebased(geometry, 0, 0)
+        ret["y"], ret["x"] = ret["y"] - yoff, ret["x"] - xoff
+    if process_full is None:
+        process_full = True
+    if process_full:
+        h, w = ret["y"].shape[-2], ret["y"].shape[-1]
+        hoff = (geometry.hImg - h) // 2
+        woff = (geometry.wImg - w) // 2
+        if _is_torch(ret["y"]):
+            full = torch.zeros((2, geometry.hImg, geometry.wImg), device=ret["y"].device)
+            fc = torch.zeros((geometry.hImg, geometry.wImg), device=ret["y"].device)
+        else:
+            full = np.zeros((2, geometry.hImg, geometry.wImg), np.float32)
+            fc = np.zeros((geometry.hImg, geometry.wImg), np.float32)
+        full[0, hoff:hoff + h, woff:woff + w] = ret["y"]
+        full[1, hoff:hoff + h, woff:woff + w] = ret["x"]
+        fc[hoff:hoff + h, woff:woff + w] = ret["confidences"]
+        ret["full"], ret["full_confidences"] = full, fc
+    return ret
+
+
+def _ones_like(x):
+    return torch.ones(x.shape, device=x.device) if _is_torch(x) else np.ones(x.shape, np.float32)
+
+
+def _floor(x):
+    return x.floor() if _is_torch(x) else np.floor(x)
+
+
+def _to_long(x):
+    return x.long() if _is_torch(x) else np.asarray(x, np.int64)
+
+
+# ------------------------------------------------------------------ multiscale
+def _ring_d(geometry, i):
+    r = geometry.ratios
+    return round_lua(geometry.maxw * (r[i] - r[i - 1]) / (2 * r[i]))
+
+
+def multiscaleLength(geometry):
+    L = geometry.maxh * geometry.maxw
+    for i in range(1, len(geometry.ratios)):
+        d = _ring_d(geometry, i)
+        L += 2 * d * geometry.maxw + 2 * (geometry.maxh - 2 * d) * d
+    return L
+
+
+# opticalflow_model_multiscale.lua:10-52
+def yx2xMulti(geometry, y, x):
+    x, y = round_lua(x), round_lua(y)
+    maxh, maxw, ratios = geometry.maxh, geometry.maxw, geometry.ratios
+
+    def is_in(size, v):
+        return -math.ceil(size / 2) + 1 <= v <= math.floor(size / 2)
+
+    for i, r in enumerate(ratios):
+        if is_in(maxw * r, x) and is_in(maxh * r, y):
+            tx = math.ceil(x / r) + math.ceil(maxw / 2)
+            ty = math.ceil(y / r) + math.ceil(maxh / 2)
+            break
+    else:
+        raise AssertionError("yx2xMulti: (%d,%d) outside every scale" % (y, x))
+    if i == 0:
+        return (ty - 1) * maxw + tx
+    d = _ring_d(geometry, i)
+    if ty <= d:
+        it = (ty - 1) * maxw + tx
+    elif ty > maxh - d:
+        it = d * maxw + 2 * (maxh - 2 * d) * d + (ty - (maxh - d) - 1) * maxw + tx
+    elif tx <= d:
+        it = d * maxw + (ty - d - 1) * d + tx
+    elif tx > maxw - d:
+        it = d * maxw + (maxh - 2 * d) * d + (ty - d - 1) * d + tx - (maxw - d)
+    else:
+        raise AssertionError("yx2xMulti: (%d,%d) falls in the removed middle" % (y, x))
+    return maxw * maxh + (i - 1) * (2 * d * maxw + 2 * (maxh - 2 * d) * d) + it
+
+
+# opticalflow_model_multiscale.lua:83-132
+def x2yxMultiNumber(geometry, x):
+    maxh, maxw, ratios = geometry.maxh, geometry.maxw, geometry.ratios
+    cy, cx = math.ceil(maxh / 2), math.ceil(maxw / 2)
+    if x <= maxh * maxw:
+        return (x - 1) // maxw + 1 - cy, (x - 1) % maxw + 1 - cx
+    x -= maxh * maxw
+    for i in range(1, len(ratios)):
+        d = _ring_d(geometry, i)
+        ln = 2 * d * maxw + 2 * (maxh - 2 * d) * d
+        side = (maxh - 2 * d) * d
+        if x > ln:
+            x -= ln
+            continue
+        if x <= d * maxw:
+            ty, tx = (x - 1) // maxw + 1, (x - 1) % maxw + 1
+        elif x - d * maxw <= side:
+            x -= d * maxw
+            ty, tx = (x - 1) // d + 1 + d, (x - 1) % d + 1
+        elif x - d * maxw - side <= side:
+            x -= d * maxw + side
+            ty, tx = (x - 1) // d + 1 + d, (x - 1) % d + 1 + maxw - d
+        else:
+            x -= d * maxw + 2 * side
+            assert x <= d * maxw
+            ty, tx = (x - 1) // maxw + 1 + maxh - d, (x - 1) % maxw + 1
+        return (ty - cy) * ratios[i], (tx - cx) * ratios[i]
+    raise AssertionError("x2yxMultiNumber: index beyond the last ring")
+
+
+def x2yxMulti2(geometry, x, bug_compat=False, ctx=None):
+    """The vectorised decode (opticalflow_model_multiscale.lua:72-81): returns (rety, retx)."""
+    args = _Args(ctx)
+    xptr, a = args.inp(x, np.int64)
+    c = args.ctx_for(a)
+    h, w = (a.shape[0], a.shape[1]) if a.ndim == 2 else (1, int(np.prod(a.shape)))
+    if bug_compat:  # entries the C falls through on keep their previous content: start from 0
+        rety = torch.zeros_like(a) if _is_torch(a) else np.zeros_like(a)
+        retx = torch.zeros_like(a) if _is_torch(a) else np.zeros_like(a)
+        yptr, xptr2 = _ptr(rety), _ptr(retx)
+    else:
+        yptr, rety = args.out(a.shape, np.int64, like=a)
+        xptr2, retx = args.out(a.shape, np.int64, like=a)
+    rat = (C.c_int * len(geometry.ratios))(*geometry.ratios)
+    check(c._lib.dm_x2yx_multi(c.handle, xptr, h, w, geometry.maxh, geometry.maxw, rat,
+                               len(geometry.ratios), 1 if bug_compat else 0, yptr, xptr2))
+    return rety, retx
+
+
+def x2yxMulti(geometry, x, ctx=None):
+    if isinstance(x, (int, float)):
+        return x2yxMultiNumber(geometry, int(x))
+    return x2yxMulti2(geometry, x, ctx=ctx)
+
+
+class MultiscaleOutput(dict):
+    pass
+
+
+class _MultiscaleModel(_Module):
+    """getModelMultiscale(geometry, full_image, prefiltered=true)
+    (opticalflow_model_multiscale.lua:175-373) + the argmax/decode of processOutput, fused.
+    forward(input): input[i] = {f1_i, f2_i}, the per-scale prefiltered maps
+    (f1_i: C x H/r x W/r after the window crop, f2_i: C x (H/r+maxh-1) x (W/r+maxw-1))."""
+
+    def __init__(self, geometry, ctx=None):
+        self.geometry, self.ctx = geometry, ctx
+        self.output = None
+
+    def updateOutput(self, inp):
+        g = self.geometry
+        n = len(g.ratios)
+        if len(inp) != n:
+            raise DepthMatchError(_lib.DM_ERR_INVALID, "one {f1,f2} pair per ratio is required")
+        args = _Args(self.ctx)
+        p1 = (C.c_void_p * n)()
+        p2 = (C.c_void_p * n)()
+        first = None
+        for i, (f1, f2) in enumerate(inp):
+            a1, t1 = args.inp(f1)
+            a2, t2 = args.inp(f2)
+            p1[i], p2[i] = a1, a2
+            first = first if first is not None else t1
+        c = args.ctx_for(first)
+        ch = first.shape[0]
+        h, w = first.shape[1] * g.ratios[0], first.shape[2] * g.ratios[0]
+        iptr, idx = args.out((h, w), np.int64, like=first)
+        yptr, fy = args.out((h, w), np.int64, like=first)
+        xptr, fx = args.out((h, w), np.int64, like=first)
+        rat = (C.c_int * n)(*g.ratios)
+        check(c._lib.dm_multiscale_extract(c.handle, p1, p2, ch, h, w, g.maxh, g.maxw, rat, n, iptr,
+                                           yptr, xptr))
+        self.output = MultiscaleOutput(index=idx, flow_y=fy, flow_x=fx)
+        return self.output
+
+
+def getModelMultiscale(geometry, full_image=True, prefiltered=True, ctx=None):
+    assert geometry.output_extraction_method in (None, "max")
+    if not prefiltered:
+        raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED, "getModelMultiscale: pass prefiltered maps "
+                              "(getMultiscalePrefilter's output)")
+    assert geometry.ratios[0] == 1
+    return _MultiscaleModel(geometry, ctx=ctx)
+
+
+# ------------------------------------------------------------------ radial
+# radial/radial_opticalflow_polar.lua:4-10
+def getRMax(h, w, e2):
+    ex, ey = float(e2[0]), float(e2[1])
+    return math.floor(math.sqrt(max(max(ex * ex + ey * ey, (w - ex) ** 2 + ey * ey),
+                                    max(ex * ex + (h - ey) ** 2, (w - ex) ** 2 + (h - ey) ** 2))))
+
+
+# radial/cartesian2polar.lua:4-49
+def getC2PMask(wsrc, hsrc, wdst, hdst, xcenter=None, ycenter=None, lpadding=0, rpadding=0, rmax=None,
+               alpha=1.0, ctx=None):
+    rmax = rmax if rmax is not None else min(hsrc // 2, wsrc // 2) - 1
+    xcenter = wsrc / 2 if xcenter is None else xcenter
+    ycenter = hsrc / 2 if ycenter is None else ycenter
+    c = ctx or default_context()
+    mask = np.empty((2, hdst, wdst + lpadding + rpadding), np.float32)
+    check(c._lib.dm_c2p_mask(c.handle, wdst, hdst, float(xcenter), float(ycenter), lpadding, rpadding,
+                             float(rmax), float(alpha), mask.ctypes.data))
+    return mask
+
+
+# radial/cartesian2polar.lua:51-89
+def getP2CMask(wsrc, hsrc, wdst, hdst, xcenter=None, ycenter=None, rmax=None, alpha=1.0, ctx=None):
+    wdst, hdst = int(wdst), int(hdst)  # torch.FloatTensor(2, hdst, wdst) truncates
+    rmax = rmax if rmax is not None else min(hdst // 2, wdst // 2) - 1
+    xcenter = wdst / 2 if xcenter is None else xcenter
+    ycenter = hdst / 2 if ycenter is None else ycenter
+    c = ctx or default_context()
+    mask = np.empty((2, hdst, wdst), np.float32)
+    check(c._lib.dm_p2c_mask(c.handle, int(wsrc), int(hsrc), wdst, hdst, float(xcenter),
+                             float(ycenter), float(rmax), float(alpha), mask.ctypes.data))
+    return mask
+
+
+# radial/cartesian2polar.lua:91-93
+def cartesian2polar(img, mask=None, ctx=None, **analytic):
+    """With `mask`: image.warp(img, mask, 'bilinear', false).  Without: the analytic remap,
+    keyword arguments as getC2PMask (wdst, hdst, xcenter, ycenter, lpadding, rpadding, rmax, alpha)."""
+    args = _Args(ctx)
+    squeeze = (img.dim() if _is_torch(img) else np.ndim(img)) == 2
+    if squeeze:
+        img = img[None]
+    sptr, s = args.inp(img)
+    c = args.ctx_for(s)
+    ch, hs, ws = s.shape
+    if mask is not None:
+        mptr, m = args.inp(mask)
+        hd, wd = m.shape[1], m.shape[2]
+        optr, out = args.out((ch, hd, wd), np.float32, like=s)
+        check(c._lib.dm_warp_bilinear(c.handle, sptr, ch, hs, ws, mptr, hd, wd, optr))
+    else:
+        wdst, hdst = analytic["wdst"], analytic["hdst"]
+        lp, rp = analytic.get("lpadding", 0), analytic.get("rpadding", 0)
+        optr, out = args.out((ch, hdst, wdst + lp + rp), np.float32, like=s)
+        check(c._lib.dm_polar_remap(c.handle, sptr, ch, hs, ws, float(analytic["xcenter"]),
+                                    float(analytic["ycenter"]), float(analytic["rmax"]),
+                                    float(analytic.get("alpha", 1.0)), lp, rp, optr, hdst, wdst))
+    return out[0] if squeeze else out
+
+
+def polar2cartesian(polar, wdst, hdst, xcenter, ycenter, rmax, alpha=1.0, ctx=None):
+    """cartesian2polar(polar, getP2CMask(wsrc, hsrc, wdst, hdst, ...)) without the LUT."""
+    args = _Args(ctx)
+    squeeze = (polar.dim() if _is_torch(polar) else np.ndim(polar)) == 2
+    if squeeze:
+        polar = polar[None]
+    sptr, s = args.inp(polar)
+    c = args.ctx_for(s)
+    ch, hs, ws = s.shape
+    optr, out = args.out((ch, int(hdst), int(wdst)), np.float32, like=s)
+    check(c._lib.dm_polar_unmap(c.handle, sptr, ch, hs, ws, float(xcenter), float(ycenter),
+                                float(rmax), float(alpha), optr, int(hdst), int(wdst)))
+    return out[0] if squeeze else out
+
+
+# radial/radial_opticalflow_polar.lua:12-30
+def getKOutput(networkp):
+    hPolar = networkp["hInput"] - math.floor((networkp["hKernel"] - 1) / 2) - networkp["hWin"] + 1
+    return hPolar / networkp["hInput"]
+
+
+def getP2CMaskOF(networkp, e2, alpha_polar=None, ctx=None):
+    wPolar = networkp["wInput"]
+    hPolar = networkp["hInput"] - networkp["hKernel"] - networkp["hWin"] + 2
+    kOutput = hPolar / networkp["hInput"]
+    wOutput, hOutput = networkp["wImg"] * kOutput, networkp["hImg"] * kOutput
+    new_e2 = (e2[0] * kOutput, e2[1] * kOutput)
+    newRMax = getRMax(networkp["hImg"], networkp["wImg"], e2) * kOutput
+    return getP2CMask(wPolar, hPolar, wOutput, hOutput, new_e2[0], new_e2[1], newRMax,
+                      1.0 if alpha_polar is None else alpha_polar, ctx=ctx)
+
+
+# radial/radial_opticalflow_display.lua:6-58
+def flow2depth(networkp, flow, center=None, kinfty=0.65, ctx=None):
+    args = _Args(ctx)
+    fptr, f = args.inp(flow)
+    c = args.ctx_for(f)
+    h, w = f.shape
+    if center is None:
+        center = (w / 2, h / 2)
+    infty = getRMax(networkp["hImg"], networkp["wImg"], center) * kinfty
+    dptr, depth = args.out((h, w), np.float32, like=f)
+    cptr, confs = args.out((h, w), np.float32, like=f)
+    check(c._lib.dm_flow2depth(c.handle, fptr, h, w, float(center[0]), float(center[1]), float(infty),
+                               dptr, cptr))
+    return depth / infty, confs

@@ -93,9 +93,11 @@ def radial_matching(in1, in2, hwin, nthreads=0):
     return out
 
 
-def neg_softmax(vol, exp_mode=0, nthreads=0):
+def neg_softmax(vol, exp_mode=0, nthreads=0, K=None):
+    """Softmax over the window: the last two dims of a (..,H1,W1,maxh,maxw) volume, else the last."""
     vol, pv = _f(vol)
-    K = vol.shape[-1] if vol.ndim == 3 else vol.shape[-1] * vol.shape[-2]
+    if K is None:
+        K = vol.shape[-1] * vol.shape[-2] if vol.ndim >= 4 else vol.shape[-1]
     rows = vol.size // K
     out = np.empty_like(vol)
     lib().orc_neg_softmax(pv, C.c_int64(rows), K, exp_mode, out.ctypes.data_as(c_fp), int(nthreads))

@@ -1,0 +1,62 @@
+"""Pins the oracle restatement against the reference's OWN native code compiled as-is
+(oracle/_ref/libdm_ref.so: version2/extract_output.cpp and x2yxMulti2.c from
+/root/reference, see oracle/Makefile).  On the GPU box /root/reference does not exist but the
+built oracle/_ref travels with the snapshot; if it is absent these tests skip and the
+committed golden vectors (tests/golden/, generated from the same _ref) still pin the oracle.
+"""
+import numpy as np
+import pytest
+
+
+def _need_ref(oracle):
+    if oracle.ref() is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+
+
+@pytest.mark.parametrize("threshold", [0.11, 0.21, 0.0, -0.5, 0.199999, 0.2, 0.9])
+@pytest.mark.parametrize("n", [1, 5, 9, 64, 289, 1089])
+def test_extract_output_matches_reference_source(oracle, threshold, n):
+    _need_ref(oracle)
+    rng = np.random.default_rng(n * 1000 + int(threshold * 100) + 7)
+    inp = rng.random((6, 11, n), dtype=np.float32) * (0.5 if n < 64 else 0.24)
+    inp[0, 0] = 0.0                      # nothing above a positive threshold
+    inp[1, 1] = inp[1, 1, 0]             # all equal: ties go through the sorting network
+    inp[2, 2, : min(n, 9)] = 0.3         # more than M qualifiers, scan-order cut-off
+    r0 = rng.integers(-5, 5, (6, 11))
+    s0 = rng.random((6, 11)).astype(np.float32)
+    a = oracle.extract_output(inp, threshold, r0, s0, "oracle")
+    b = oracle.extract_output(inp, threshold, r0, s0, "ref")
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("threshold,acc", [(0.11, 0.5), (0.21, 1.0), (0.05, 0.0)])
+def test_extract_output_marginalized_matches_reference_source(oracle, threshold, acc):
+    _need_ref(oracle)
+    rng = np.random.default_rng(3)
+    inp = rng.random((9, 7, 33), dtype=np.float32) * 0.3
+    r0 = rng.integers(0, 9, (9, 7))
+    a = oracle.extract_output_marginalized(inp, threshold, acc, r0, "oracle")
+    b = oracle.extract_output_marginalized(inp, threshold, acc, r0, "ref")
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("maxh,maxw,ratios", [(8, 8, [1, 2]), (8, 8, [1, 2, 4]), (16, 16, [1, 2, 4]),
+                                             (9, 7, [1, 3]), (8, 8, [1]), (12, 8, [1, 2])])
+def test_x2yxmulti2_bugcompat_matches_reference_source(oracle, maxh, maxw, ratios):
+    _need_ref(oracle)
+    L = oracle.multiscale_length(maxh, maxw, ratios)
+    x = np.arange(-2, L + 40 + (L % 2), dtype=np.int64).reshape(2, -1)
+    a = oracle.x2yx_multi2_bugcompat(x, maxh, maxw, ratios, "oracle")
+    b = oracle.x2yx_multi2_bugcompat(x, maxh, maxw, ratios, "ref")
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_reference_c_decode_diverges_from_lua_spec(oracle):
+    """Documents SURVEY 8a-11: the shipped C is not the Lua spec (e.g. index 64 of an 8x8 window)."""
+    ry, rx = oracle.x2yx_multi2_bugcompat(np.array([[64]]), 8, 8, [1, 2])
+    rc, sy, sx = oracle.x2yx_multi_number(8, 8, [1, 2], 64)
+    assert rc == 0 and (sy, sx) == (4, 4)
+    assert (int(ry[0, 0]), int(rx[0, 0])) != (sy, sx)
