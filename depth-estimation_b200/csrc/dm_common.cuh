@@ -56,6 +56,8 @@ struct dm_ctx {
   cudaStream_t stream = nullptr;
   dm::Arena arena;       // device scratch + staging, bump-allocated per call
   int64_t launches = 0;  // kernels launched through this context
+  bool profiling = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the sweep kernel when profiling
   // pending device->host copies of the current call
   struct Pending {
     void *host;
@@ -88,6 +90,12 @@ struct Call {
 int ensure_arena(dm_ctx *ctx, size_t bytes);
 
 inline void count_launch(dm_ctx *ctx, int n = 1) { ctx->launches += n; }
+inline void prof_begin(dm_ctx *ctx) {
+  if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream);
+}
+inline void prof_end(dm_ctx *ctx) {
+  if (ctx->profiling) cudaEventRecord(ctx->ev1, ctx->stream);
+}
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda, so the
 // library still loads on a box without a driver).

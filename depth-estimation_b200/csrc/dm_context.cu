@@ -223,6 +223,8 @@ int dm_destroy(dm_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   delete ctx;
   return DM_OK;
 }
@@ -254,5 +256,24 @@ int dm_host_free(void *ptr) {
 }
 
 int64_t dm_launch_count(dm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dm_set_profiling(dm_ctx *ctx, int on) {
+  DM_REQUIRE(ctx != nullptr, "dm_set_profiling: ctx is NULL");
+  DM_CUDA(cudaSetDevice(ctx->device));
+  if (on && !ctx->ev0) {
+    DM_CUDA(cudaEventCreate(&ctx->ev0));
+    DM_CUDA(cudaEventCreate(&ctx->ev1));
+  }
+  ctx->profiling = on != 0;
+  return DM_OK;
+}
+
+int dm_last_kernel_ms(dm_ctx *ctx, float *ms) {
+  DM_REQUIRE(ctx && ms, "dm_last_kernel_ms: NULL argument");
+  DM_REQUIRE(ctx->ev0 != nullptr, "dm_last_kernel_ms: profiling was never switched on");
+  DM_CUDA(cudaEventSynchronize(ctx->ev1));
+  DM_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return DM_OK;
+}
 
 }  // extern "C"

@@ -532,7 +532,9 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
   P.cand_v = static_cast<float *>(scratch);
   P.cand_k = reinterpret_cast<int *>(P.cand_v + (size_t)grid * kThreads * kP * kNC);
   void *args[] = {(void *)&pr.tmap, (void *)&P};
+  prof_begin(ctx);
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+  prof_end(ctx);
   count_launch(ctx);
   return call.finish();
 }
@@ -623,7 +625,9 @@ extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int max
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = grid_for(ctx, kfn, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&P};
+  prof_begin(ctx);
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+  prof_end(ctx);
   count_launch(ctx);
   return call.finish();
 }

@@ -49,6 +49,8 @@ SIGNATURES = {
     "dm_host_alloc": (_I, [C.POINTER(_P), C.c_size_t]),
     "dm_host_free": (_I, [_P]),
     "dm_launch_count": (_L, [_P]),
+    "dm_set_profiling": (_I, [_P, _I]),
+    "dm_last_kernel_ms": (_I, [_P, C.POINTER(_F)]),
     "dm_match_volume": (_I, [_P, C.POINTER(dm_pair), _I, _I, _I, _P]),
     "dm_match_extract": (_I, [_P, C.POINTER(dm_pair), _I, _I, C.c_uint, _D, _I, _I,
                               C.POINTER(dm_extract_out)]),

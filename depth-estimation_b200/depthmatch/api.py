@@ -66,6 +66,14 @@ class Context:
     def launch_count(self):
         return int(self._lib.dm_launch_count(self._h))
 
+    def set_profiling(self, on=True):
+        check(self._lib.dm_set_profiling(self._h, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        check(self._lib.dm_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def use_stream(self, cuda_stream):
         """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
         if cuda_stream != self._stream:

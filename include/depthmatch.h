@@ -59,6 +59,10 @@ int dm_host_alloc(void **ptr, size_t bytes);
 int dm_host_free(void *ptr);
 /* number of CUDA kernels this context has launched so far (bench.py: gpu_launches) */
 int64_t dm_launch_count(dm_ctx *ctx);
+/* CUDA-event timing of the dominant kernel of a call (the matching sweep): switch it on,
+ * make calls, read the duration of the most recent sweep kernel in milliseconds */
+int dm_set_profiling(dm_ctx *ctx, int on);
+int dm_last_kernel_ms(dm_ctx *ctx, float *ms);
 
 /* ---- inputs ------------------------------------------------------------- */
 /* Two stacks of feature maps.  in1 is the (already window-cropped) frame-1 map

@@ -1,0 +1,90 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/depthmatch.h
+declares; the host-side index helpers agree with the oracle.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "depthmatch.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(dm):
+    lib = dm.load()
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libdepthmatch.so does not export %s" % n
+    from depthmatch import _lib
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+
+
+def test_struct_layout_matches_header(dm):
+    from depthmatch import _lib
+    assert C.sizeof(_lib.dm_pair) == 2 * 8 + 6 * 4 + 6 * 8
+    assert C.sizeof(_lib.dm_extract_out) == 8 * 8
+
+
+def test_version_and_error_string(dm):
+    lib = dm.load()
+    assert lib.dm_version() == 100
+    assert isinstance(lib.dm_last_error(), bytes)
+
+
+def test_fails_loudly_without_a_device(dm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(dm.DepthMatchError) as e:
+        dm.Context(0)
+    assert "no CPU fallback" in str(e.value)
+    # and the public API does not quietly compute on the CPU either
+    with pytest.raises(dm.DepthMatchError):
+        dm.match_extract(np.zeros((1, 4, 4), np.float32), np.zeros((1, 6, 6), np.float32), 3, 3)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "depth-estimation_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".lua")):
+                txt = open(os.path.join(d, f)).read()
+                assert "oracle_lib" not in txt and "libdm_oracle" not in txt and "orc_" not in txt, f
+
+
+@pytest.mark.parametrize("ratios", [[1, 2], [1, 2, 4]])
+def test_python_index_helpers_match_oracle(dm, oracle, ratios):
+    g = dm.Geometry(maxh=8, maxw=8, ratios=ratios, multiscale=True)
+    L = dm.multiscaleLength(g)
+    assert L == oracle.multiscale_length(8, 8, ratios)
+    for i in range(1, L + 1):
+        y, x = dm.x2yxMultiNumber(g, i)
+        rc, oy, ox = oracle.x2yx_multi_number(8, 8, ratios, i)
+        assert rc == 0 and (y, x) == (oy, ox)
+        assert dm.yx2xMulti(g, y, x) == i == oracle.yx2x_multi(8, 8, ratios, y, x)
+    assert dm.getMiddleIndex(g) == 28
+
+
+def test_single_scale_index_helpers(dm):
+    g = dm.Geometry(maxh=17, maxw=33)
+    assert dm.getMiddleIndex(g) == (9 - 1) * 33 + 17
+    assert dm.x2yx(g, dm.yx2x(g, 5, 7)) == (5, 7)
+    y, x = dm.x2yx(g, np.array([[1, 33, 34, 17 * 33]]))
+    np.testing.assert_array_equal(y, [[1, 1, 2, 17]])
+    np.testing.assert_array_equal(x, [[1, 33, 1, 33]])
+    assert dm.centered2onebased(g, 0, 0) == (9, 17)
+
+
+def test_prepare_input_is_a_view_with_the_reference_offsets(dm):
+    g = dm.Geometry(maxh=5, maxw=8)
+    f1 = np.arange(2 * 20 * 30, dtype=np.float32).reshape(2, 20, 30)
+    a, b = dm.prepareInput(g, f1, f1)
+    assert a.shape == (2, 16, 23) and b is f1
+    assert np.shares_memory(a, f1) and a[0, 0, 0] == f1[0, 2, 3]  # ceil(5/2)-1, ceil(8/2)-1

@@ -1,0 +1,399 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical seeded
+inputs.  Bars (BASELINE.json north_star): integer indices bit-exact, except pixels whose
+top-2 softmax scores differ by < 1e-5 relative (counted and reported); fp32 scores within
+1e-4 relative.  With DM_FLAG_EXACT_SSD the SSD itself is bit-exact."""
+import math
+
+import numpy as np
+import pytest
+
+from synth import make_pair
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4          # fp32 scores (north_star)
+NEAR_TIE = 1e-5      # relative top-2 gap below which an index may differ (north_star)
+
+
+def oracle_outputs(oracle, in1, in2, maxh, maxw, thr=0.11):
+    K = maxh * maxw
+    vol = oracle.spatial_matching(in1, in2, maxh, maxw)
+    prob = oracle.neg_softmax(vol)
+    cy, cx = math.ceil(maxh / 2), math.ceil(maxw / 2)
+    middle = (cy - 1) * maxw + cx
+    idx, pmax = oracle.argmax_tie(prob, K, middle)
+    shp = in1.shape[1:]
+    ret, sc, _ = oracle.extract_output(prob.reshape(shp + (K,)), thr)
+    ym, xm = oracle.soft_mean(prob, maxh, maxw)
+    gap = oracle.top2_relgap(prob, K)
+    return dict(vol=vol, prob=prob, index=idx.reshape(shp), pmax=pmax.reshape(shp),
+                min_ssd=vol.reshape(shp + (K,)).min(-1), index_thr=ret, score_thr=sc,
+                soft_y=ym.reshape(shp), soft_x=xm.reshape(shp), gap=gap.reshape(shp), middle=middle)
+
+
+def check_fused(oracle, got, want, exact, thr=0.11):
+    tie = want["gap"] < NEAR_TIE
+    bad = (got["index"] != want["index"]) & ~tie
+    assert bad.sum() == 0, "%d index mismatches outside near-ties (near-ties: %d)" % (bad.sum(), tie.sum())
+    if exact:
+        np.testing.assert_array_equal(got["min_ssd"], want["min_ssd"])
+    else:
+        np.testing.assert_allclose(got["min_ssd"], want["min_ssd"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(got["pmax"], want["pmax"], rtol=RTOL)
+    np.testing.assert_allclose(got["soft_yx"][0], want["soft_y"], rtol=RTOL)
+    np.testing.assert_allclose(got["soft_yx"][1], want["soft_x"], rtol=RTOL)
+    # thresholded extraction: a probability within 1e-5 relative of the threshold may flip
+    prob = want["prob"].reshape(want["index"].shape + (-1,))
+    edge = (np.abs(prob - thr) < thr * 1e-5 * 4).any(-1) | tie
+    ok = ~edge
+    np.testing.assert_array_equal(got["index_thr"][ok], want["index_thr"][ok])
+    np.testing.assert_allclose(got["score_thr"][ok], want["score_thr"][ok], rtol=RTOL, atol=1e-7)
+    return int(tie.sum())
+
+
+CASES = [
+    # C, H2, W2, maxh, maxw
+    (10, 40, 60, 17, 17),
+    (10, 50, 170, 33, 33),    # more than one tile in x, tail block of 9
+    (3, 21, 37, 5, 7),        # ragged, W2 not a multiple of 4 (repack path), CT=4
+    (1, 12, 20, 1, 1),        # degenerate 1x1 window
+    (4, 30, 45, 8, 8),
+    (10, 30, 50, 16, 16),
+    (16, 26, 44, 9, 10),      # CT=16, tail block of 2
+    (7, 40, 90, 15, 65),      # widest window
+    (20, 24, 30, 6, 6),       # > 16 channels: untiled kernel
+]
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("case", CASES)
+def test_fused_match_extract_vs_oracle(dm, oracle, case, exact):
+    C, H2, W2, maxh, maxw = case
+    in1, in2, _ = make_pair(C, H2, W2, maxh, maxw, seed=11, noise=0.3)
+    want = oracle_outputs(oracle, in1, in2, maxh, maxw)
+    got = dm.match_extract(in1, in2, maxh, maxw, exact=exact,
+                           want=("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx",
+                                 "n_untouched"))
+    check_fused(oracle, got, want, exact)
+    assert int(got["n_untouched"]) >= int((want["index_thr"] == 0).sum()) - 4
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.05])
+def test_planted_flow_is_recovered(dm, noise):
+    """T2 on the GPU path: the planted integer flow is the known answer."""
+    maxh = maxw = 17
+    in1, in2, flow = make_pair(10, 80, 120, maxh, maxw, seed=3, noise=noise)
+    got = dm.match_extract(in1, in2, maxh, maxw, canvas=(80, 120), want=("index",))
+    full = got["flow_full"]
+    hoff, woff = (80 - in1.shape[1]) // 2, (120 - in1.shape[2]) // 2
+    np.testing.assert_array_equal(full[0, hoff:hoff + in1.shape[1], woff:woff + in1.shape[2]], flow[0])
+    np.testing.assert_array_equal(full[1, hoff:hoff + in1.shape[1], woff:woff + in1.shape[2]], flow[1])
+    assert full[:, :hoff].sum() == 0 and full[:, hoff + in1.shape[1]:].sum() == 0
+
+
+def test_zero_flow_tie_rule(dm, oracle):
+    """Constant frames: every window entry ties, the middle index must win
+    (opticalflow_model.lua:157-159), and softmax is uniform."""
+    maxh, maxw = 5, 9
+    in2 = np.ones((3, 20, 40), np.float32)
+    in1 = np.ones((3, 16, 32), np.float32)
+    got = dm.match_extract(in1, in2, maxh, maxw, want=("index", "pmax", "index_thr", "score_thr"))
+    want = oracle_outputs(oracle, in1, in2, maxh, maxw)
+    np.testing.assert_array_equal(got["index"], want["index"])
+    assert (got["index"] == want["middle"]).all()
+    np.testing.assert_allclose(got["pmax"], 1.0 / 45, rtol=1e-5)
+    assert (got["index_thr"] == 0).all() and (got["score_thr"] == 0).all()
+    got = dm.match_extract(in1, in2, maxh, maxw, tie_middle=False, want=("index",))
+    assert (got["index"] == 1).all()
+
+
+def test_small_window_all_qualify_scan_order(dm, oracle):
+    """3x3 window of equal SSDs: p = 1/9 > 0.11 for all nine, extractOutput keeps the FIRST 8."""
+    in2 = np.zeros((2, 10, 12), np.float32)
+    in1 = np.zeros((2, 8, 10), np.float32)
+    want = oracle_outputs(oracle, in1, in2, 3, 3)
+    got = dm.match_extract(in1, in2, 3, 3, want=("index_thr", "score_thr"))
+    np.testing.assert_array_equal(got["index_thr"], want["index_thr"])
+    np.testing.assert_allclose(got["score_thr"], want["score_thr"], rtol=1e-6)
+
+
+def test_batched_strided_and_device_inputs(dm, oracle):
+    """N > 1, in1 given as the strided crop prepareInput returns, torch CUDA tensors in and out."""
+    import torch
+    maxh, maxw, C = 9, 17, 10
+    frames = []
+    for n in range(3):
+        in1, in2, _ = make_pair(C, 40, 72, maxh, maxw, seed=20 + n, noise=0.2)
+        full1 = np.random.default_rng(n).standard_normal((C, 40, 72)).astype(np.float32)
+        oy, ox = math.ceil(maxh / 2) - 1, math.ceil(maxw / 2) - 1
+        full1[:, oy:oy + in1.shape[1], ox:ox + in1.shape[2]] = in1
+        frames.append((full1, in2, in1))
+    f1 = np.stack([f[0] for f in frames])
+    f2 = np.stack([f[1] for f in frames])
+    g = dm.Geometry(maxh=maxh, maxw=maxw)
+    oy, ox = math.ceil(maxh / 2) - 1, math.ceil(maxw / 2) - 1
+    H1, W1 = 40 - maxh + 1, 72 - maxw + 1
+    view = f1[:, :, oy:oy + H1, ox:ox + W1]
+    host = dm.match_extract(view, f2, maxh, maxw, exact=True, want=("index", "min_ssd"))
+    t1 = torch.from_numpy(f1).cuda()[:, :, oy:oy + H1, ox:ox + W1]
+    t2 = torch.from_numpy(f2).cuda()
+    dev = dm.match_extract(t1, t2, maxh, maxw, exact=True, want=("index", "min_ssd"))
+    torch.cuda.synchronize()
+    for n in range(3):
+        want = oracle_outputs(oracle, frames[n][2], frames[n][1], maxh, maxw)
+        tie = want["gap"] < NEAR_TIE
+        assert ((host["index"][n] != want["index"]) & ~tie).sum() == 0
+        np.testing.assert_array_equal(host["min_ssd"][n], want["min_ssd"])
+        np.testing.assert_array_equal(dev["index"][n].cpu().numpy(), host["index"][n])
+        np.testing.assert_array_equal(dev["min_ssd"][n].cpu().numpy(), host["min_ssd"][n])
+
+
+@pytest.mark.parametrize("case", [(10, 30, 150, 9, 17), (3, 19, 23, 4, 5), (20, 16, 20, 3, 4)])
+def test_volume_ssd_and_softmax_vs_oracle(dm, oracle, case):
+    C, H2, W2, maxh, maxw = case
+    in1, in2, _ = make_pair(C, H2, W2, maxh, maxw, seed=2, noise=0.5)
+    vol = oracle.spatial_matching(in1, in2, maxh, maxw)
+    got = dm.nn.SpatialMatching(maxh, maxw, False, exact=True).forward([in1, in2])
+    np.testing.assert_array_equal(got, vol)
+    got = dm.nn.SpatialMatching(maxh, maxw).forward([in1, in2])
+    np.testing.assert_allclose(got, vol, rtol=RTOL, atol=1e-6)
+    prob = oracle.neg_softmax(vol)
+    gotp = dm.match_volume(in1, in2, maxh, maxw, softmax=True)
+    np.testing.assert_allclose(gotp, prob, rtol=RTOL, atol=1e-9)
+    # stand-alone softmax on a volume in memory
+    from depthmatch import api
+    a = api._Args()
+    K = maxh * maxw
+    out = np.empty_like(vol)
+    c = dm.default_context()
+    api.check(c._lib.dm_neg_softmax(c.handle, vol.ctypes.data, vol.size // K, K, out.ctypes.data))
+    np.testing.assert_allclose(out, prob, rtol=1e-5, atol=1e-12)
+
+
+def test_module_level_process_output_vs_oracle(dm, oracle):
+    """getModel(prefiltered) -> forward -> processOutput for 'max', 'max'+threshold and 'mean'."""
+    maxh, maxw = 9, 9
+    in1, in2, _ = make_pair(10, 40, 56, maxh, maxw, seed=8, noise=0.3)
+    want = oracle_outputs(oracle, in1, in2, maxh, maxw)
+    g = dm.Geometry(maxh=maxh, maxw=maxw, hImg=40, wImg=56, output_extraction_method="max")
+    model = dm.getModel(g, True, True)
+    prob = model.forward([in1, in2])
+    np.testing.assert_allclose(prob.reshape(want["prob"].shape), want["prob"], rtol=RTOL, atol=1e-9)
+    # feed the ORACLE's volume so that the stand-alone kernels are checked bit for bit
+    oprob = want["prob"].reshape(in1.shape[1:] + (maxh * maxw,))
+    out = dm.processOutput(g, oprob, True, None)
+    np.testing.assert_array_equal(out["index"], want["index"])
+    full = oracle.flow_canvas(want["index"], in1.shape[1], in1.shape[2], maxh, maxw, 40, 56)
+    np.testing.assert_array_equal(out["full"], full)
+    out = dm.processOutput(g, oprob, True, 2)
+    np.testing.assert_array_equal(out["index"], want["index_thr"])
+    np.testing.assert_array_equal(out["confidences"], want["score_thr"] > 2)
+    g.output_extraction_method = "mean"
+    out = dm.processOutput(g, oprob, True, None)
+    cy = math.ceil(maxh / 2)
+    np.testing.assert_array_equal(out["y"] + cy, want["soft_y"])
+    np.testing.assert_array_equal(out["x"] + cy, want["soft_x"])
+    pm = oracle.marginal_x(want["prob"], maxh, maxw).reshape(in1.shape[1:] + (maxh,))
+    _, sc, _ = oracle.extract_output(pm, 0.11)
+    np.testing.assert_array_equal(out["confidences"], sc > 0)
+    # and the fused module gives the same answers without the volume
+    g.output_extraction_method = "max"
+    fused = dm.getModel(g, True, True, fused=True).forward([in1, in2])
+    out = dm.processOutput(g, fused, True, None)
+    tie = want["gap"] < NEAR_TIE
+    assert ((out["index"] != want["index"]) & ~tie).sum() == 0
+
+
+@pytest.mark.parametrize("threshold", [0.11, 0.21, 0.0, -0.5])
+@pytest.mark.parametrize("n", [5, 33, 289, 1089])
+def test_extract_output_standalone_bit_exact(dm, oracle, threshold, n):
+    rng = np.random.default_rng(n)
+    inp = rng.random((13, 17, n), dtype=np.float32) * (0.5 if n < 64 else 0.24)
+    inp[0, 0] = 0
+    inp[1, 1] = inp[1, 1, 0]
+    r0 = rng.integers(-5, 5, (13, 17)).astype(np.int64)
+    s0 = rng.random((13, 17)).astype(np.float32)
+    wr, ws, written = oracle.extract_output(inp, threshold, r0, s0)
+    ret, sc = r0.copy(), s0.copy()
+    nun = dm.extractoutput.extractOutput(inp, sc, threshold, ret)
+    np.testing.assert_array_equal(ret, wr)
+    np.testing.assert_array_equal(sc, ws)
+    assert nun == 13 * 17 - written
+    wr, wg = oracle.extract_output_marginalized(inp, threshold, 0.5, r0)
+    ret, gd = r0.copy(), np.full((13, 17), 9, np.int64)
+    dm.extractoutput.extractOutputMarginalized(inp, threshold, 0.5, ret, gd)
+    np.testing.assert_array_equal(ret, wr)
+    np.testing.assert_array_equal(gd, wg)
+
+
+def test_radial_matching_vs_oracle(dm, oracle):
+    """c4's matcher: polar maps 10 x 384 x 400 cropped by hWin-1 rows, hWin = 15 (smaller here)."""
+    rng = np.random.default_rng(9)
+    C, Hp, Wp, hWin = 10, 64, 80, 15
+    f2 = rng.standard_normal((C, Hp, Wp)).astype(np.float32)
+    f1 = np.roll(f2, -4, axis=1)[:, : Hp - hWin + 1] + 0.05 * rng.standard_normal((C, Hp - hWin + 1, Wp)).astype(np.float32)
+    vol = oracle.radial_matching(f1, f2, hWin)
+    m = dm.nn.SpatialRadialMatching(hWin)
+    np.testing.assert_array_equal(m.forward([f1, f2]), vol)
+    idx, mn = oracle.argmin_tie(vol, hWin, 0)
+    flow, gmin = m.argmin_flow([f1, f2])
+    np.testing.assert_array_equal(flow, (idx - 1).reshape(flow.shape).astype(np.float32))
+    np.testing.assert_array_equal(gmin, mn.reshape(flow.shape))
+    assert (flow == 4).mean() > 0.99
+
+
+@pytest.mark.parametrize("maxh,maxw,ratios", [(8, 8, [1, 2]), (8, 8, [1, 2, 4]), (16, 16, [1, 2, 4])])
+def test_x2yx_multi_both_modes(dm, oracle, maxh, maxw, ratios):
+    g = dm.Geometry(maxh=maxh, maxw=maxw, ratios=ratios, multiscale=True)
+    L = dm.multiscaleLength(g)
+    x = np.arange(1, L + 1, dtype=np.int64).reshape(4, -1)
+    ry, rx = dm.x2yxMulti(g, x)
+    for i, (a, b) in enumerate(zip(ry.reshape(-1), rx.reshape(-1))):
+        rc, oy, ox = oracle.x2yx_multi_number(maxh, maxw, ratios, i + 1)
+        assert (a, b) == (oy, ox)
+    xb = np.arange(-2, L + 38 + (L % 2), dtype=np.int64).reshape(2, -1)
+    wy, wx = oracle.x2yx_multi2_bugcompat(xb, maxh, maxw, ratios, fill=0)
+    gy, gx = dm.x2yxMulti2(g, xb, bug_compat=True)
+    np.testing.assert_array_equal(gy, wy)
+    np.testing.assert_array_equal(gx, wx)
+
+
+def test_cascade_add_vs_oracle(dm, oracle):
+    rng = np.random.default_rng(12)
+    for ratios, k in (([1, 2, 4], 8), ([1, 2], 8), ([1, 2, 4], 16), ([1, 3], 12)):
+        inp = rng.random((len(ratios), 37, k, k)).astype(np.float32)
+        want = oracle.cascade_add(inp, ratios)
+        got = dm.nn.CascadingAddTable(ratios).forward([inp[i] for i in range(len(ratios))])
+        for i in range(len(ratios)):
+            np.testing.assert_array_equal(got[i], want[i])
+    with pytest.raises(dm.DepthMatchError):
+        dm.nn.CascadingAddTable([1, 2]).forward([inp[0][:, :7, :7], inp[1][:, :7, :7]])
+
+
+def _multiscale_oracle(oracle, f1s, f2s, maxh, maxw, ratios):
+    K = maxh * maxw
+    per = []
+    for (f1, f2, r) in zip(f1s, f2s, ratios):
+        vol = oracle.spatial_matching(f1, f2, maxh, maxw)
+        prob = oracle.neg_softmax(vol).reshape(f1.shape[1], f1.shape[2], K)
+        per.append(oracle.upsample_nearest_rows(prob, r).reshape(-1, maxh, maxw))
+    casc = oracle.cascade_add(np.stack(per), ratios)
+    vec = oracle.ring_join(casc, ratios)
+    middle = oracle.yx2x_multi(maxh, maxw, ratios, 0, 0)
+    idx, _ = oracle.argmax_tie(vec, vec.shape[1], middle)
+    gap = oracle.top2_relgap(vec, vec.shape[1])
+    fy = np.empty_like(idx)
+    fx = np.empty_like(idx)
+    for i, v in enumerate(idx):
+        _, fy[i], fx[i] = oracle.x2yx_multi_number(maxh, maxw, ratios, int(v))
+    return idx, fy, fx, gap
+
+
+@pytest.mark.parametrize("ratios", [[1, 2], [1, 2, 4]])
+def test_multiscale_extract_vs_oracle(dm, oracle, ratios):
+    """c3 in small: per-scale prefiltered maps -> matching -> softmax -> cascade -> ring ->
+    argmax (middle tie rule) -> decode."""
+    rng = np.random.default_rng(14)
+    maxh = maxw = 8
+    C, H, W = 10, 32, 48
+    f1s, f2s = [], []
+    for r in ratios:
+        h, w = H // r, W // r
+        f2 = rng.standard_normal((C, h + maxh - 1, w + maxw - 1)).astype(np.float32)
+        f1 = f2[:, 3:3 + h, 3:3 + w] + 0.4 * rng.standard_normal((C, h, w)).astype(np.float32)
+        f1s.append(np.ascontiguousarray(f1))
+        f2s.append(f2)
+    g = dm.Geometry(maxh=maxh, maxw=maxw, ratios=ratios, multiscale=True, hImg=H, wImg=W,
+                    output_extraction_method="max")
+    out = dm.getModelMultiscale(g, True, True).forward(list(zip(f1s, f2s)))
+    idx, fy, fx, gap = _multiscale_oracle(oracle, f1s, f2s, maxh, maxw, ratios)
+    tie = gap < NEAR_TIE * 10
+    bad = (out["index"].reshape(-1) != idx) & ~tie
+    assert bad.sum() == 0, (bad.sum(), tie.sum())
+    ok = ~tie
+    np.testing.assert_array_equal(out["flow_y"].reshape(-1)[ok], fy[ok])
+    np.testing.assert_array_equal(out["flow_x"].reshape(-1)[ok], fx[ok])
+    po = dm.processOutput(g, out, True, None)
+    assert po["full"].shape == (2, H, W)
+
+
+def test_downsample_avg(dm, oracle):
+    rng = np.random.default_rng(15)
+    img = rng.random((3, 24, 36)).astype(np.float32)
+    from depthmatch import api
+    c = dm.default_context()
+    for r in (1, 2, 4):
+        out = np.empty((3, 24 // r, 36 // r), np.float32)
+        api.check(c._lib.dm_downsample_avg(c.handle, img.ctypes.data, 3, 24, 36, r, out.ctypes.data))
+        np.testing.assert_array_equal(out, oracle.downsample_avg(img, r))
+
+
+def test_polar_remap_vs_oracle(dm, oracle):
+    """c4's remap at reduced size, epipole from radial/gopro.cal scaled."""
+    rng = np.random.default_rng(16)
+    hImg, wImg, hIn, wIn, wK = 90, 160, 100, 100, 17
+    e2 = (641.4552 * wImg / 1280.0, 344.950836 * wImg / 1280.0)
+    img = rng.random((3, hImg, wImg)).astype(np.float32)
+    rmax = dm.getRMax(hImg, wImg, e2)
+    assert rmax == oracle.get_rmax(hImg, wImg, *e2)
+    lp, rp = (wK - 1) // 2, math.ceil((wK - 1) / 2)
+    omask = oracle.c2p_mask(wIn, hIn, e2[0], e2[1], lp, rp, rmax, 1.0)
+    gmask = dm.getC2PMask(wImg, hImg, wIn, hIn, e2[0], e2[1], lp, rp, rmax, 1.0)
+    # CUDA's double sin/cos/pow are within 1-2 ulp of glibc's: coordinates agree to float rounding
+    np.testing.assert_allclose(gmask, omask, rtol=0, atol=2e-5)
+    want = oracle.warp_bilinear(img, omask)
+    np.testing.assert_array_equal(dm.cartesian2polar(img, omask), want)          # LUT path, bit-exact
+    got = dm.cartesian2polar(img, wdst=wIn, hdst=hIn, xcenter=e2[0], ycenter=e2[1], lpadding=lp,
+                             rpadding=rp, rmax=rmax, alpha=1.0)                  # analytic path
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-4)
+    # inverse
+    pol = want[:, :, lp:lp + wIn]
+    om2 = oracle.p2c_mask(wIn, hIn, wImg, hImg, e2[0], e2[1], rmax, 1.0)
+    gm2 = dm.getP2CMask(wIn, hIn, wImg, hImg, e2[0], e2[1], rmax, 1.0)
+    np.testing.assert_allclose(gm2, om2, rtol=0, atol=5e-5)
+    back = oracle.warp_bilinear(pol, om2)
+    np.testing.assert_allclose(dm.polar2cartesian(pol, wImg, hImg, e2[0], e2[1], rmax), back, rtol=0,
+                               atol=2e-4)
+    flow = rng.random((hImg, wImg)).astype(np.float32) * 3
+    netp = dict(hImg=hImg, wImg=wImg)
+    infty = dm.getRMax(hImg, wImg, e2) * 0.65
+    d, c = oracle.flow2depth(flow, e2[0], e2[1], infty)
+    gd, gc = dm.flow2depth(netp, flow, e2, 0.65)
+    np.testing.assert_array_equal(gc, c)
+    np.testing.assert_allclose(gd, d / np.float32(infty), rtol=1e-6)
+
+
+def test_argument_errors_are_reported_not_crashed(dm):
+    a = np.zeros((2, 8, 8), np.float32)
+    b = np.zeros((2, 9, 9), np.float32)
+    with pytest.raises(dm.DepthMatchError) as e:
+        dm.match_extract(a, b, 5, 5)
+    assert e.value.status == -1 and "smaller than" in str(e.value)
+    with pytest.raises(dm.DepthMatchError):
+        dm.match_extract(a, np.zeros((3, 12, 12), np.float32), 5, 5)
+    with pytest.raises(dm.DepthMatchError):
+        dm.match_extract(a, np.zeros((2, 12, 12), np.float32), 5, 5, prob_threshold=0.05)
+
+
+def test_north_config_full_size_properties(dm):
+    """640x360, 33x33, C=10 (BASELINE north): too big for the oracle in seconds, so check
+    size-independent properties: the planted flow is recovered, probabilities are in (0,1],
+    soft means lie inside the window, and the exact and FMA paths agree on every index that is
+    not a near tie."""
+    maxh = maxw = 33
+    in1, in2, flow = make_pair(10, 360, 640, maxh, maxw, seed=1234, noise=0.05)
+    got = dm.match_extract(in1, in2, maxh, maxw, canvas=(360, 640),
+                           want=("index", "min_ssd", "pmax", "soft_yx", "index_thr", "score_thr"))
+    cy = 17
+    fy = (got["index"] - 1) // maxw + 1 - cy
+    fx = (got["index"] - 1) % maxw + 1 - cy
+    np.testing.assert_array_equal(fy, flow[0])
+    np.testing.assert_array_equal(fx, flow[1])
+    assert (got["pmax"] > 0).all() and (got["pmax"] <= 1.0 + 1e-6).all()
+    assert (got["soft_yx"] >= 1 - 1e-4).all() and (got["soft_yx"] <= maxh + 1e-4).all()
+    np.testing.assert_array_equal(got["flow_full"][0, 16:16 + 328, 16:16 + 608], flow[0])
+    # with sigma 0.05 noise the winner takes nearly all the mass: thresholded == WTA
+    assert (got["index_thr"] == got["index"]).mean() > 0.999
+    ex = dm.match_extract(in1, in2, maxh, maxw, exact=True, want=("index", "min_ssd"))
+    np.testing.assert_array_equal(ex["index"], got["index"])
+    np.testing.assert_allclose(ex["min_ssd"], got["min_ssd"], rtol=RTOL)
