@@ -73,6 +73,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi's start-up takes driver locks: let it settle before anything is timed."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
     def mark(self):
         return len(self.rows)
 
@@ -165,7 +171,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frame pairs per GPU per step")
@@ -211,6 +217,8 @@ def main():
         return dm.match_extract(in1, f2, MAXH, MAXW, canvas=(H, W), want=want, ctx=ctx)
 
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
     for _ in range(args.warmup):
         step()
     barrier()

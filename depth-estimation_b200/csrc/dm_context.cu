@@ -238,7 +238,14 @@ int dm_synchronize(dm_ctx *ctx) {
 int dm_set_stream(dm_ctx *ctx, void *cuda_stream) {
   DM_REQUIRE(ctx != nullptr, "dm_set_stream: ctx is NULL");
   DM_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);  // NULL is CUDA's legacy default stream
+  return DM_OK;
+}
+
+int dm_reset_stream(dm_ctx *ctx) {
+  DM_REQUIRE(ctx != nullptr, "dm_reset_stream: ctx is NULL");
+  DM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = ctx->own_stream;
   return DM_OK;
 }
 

@@ -18,27 +18,277 @@
 
 namespace dm {
 
-constexpr int kBarBytes = 128;  // room for the kNSlot mbarriers, keeps what follows 16-byte aligned
-constexpr int kNC = 9;  // candidate entries per pixel: at most 9 probabilities can exceed 0.1
+constexpr int kBarBytes = 384;  // room for the 2*kNSlot mbarriers, keeps what follows 128-byte aligned
 
 struct ExtractParams {
   SweepGeom g;
   unsigned flags;
-  double thr;         // probability threshold of extractOutput
-  float cand_margin;  // ln(1/thr) + slack: v_k < min + margin is necessary for p_k > thr
   int M;              // 8 if thr < 0.2 else 4 (extract_output.cpp:82-84)
-  int mid_dy, mid_dx, middle;  // zero-flow entry (0-based dy,dx; 1-based index)
-  int cy, cx;                  // ceil(maxh/2), ceil(maxw/2)
+  float p_none;       // a probability below this is below the threshold for sure (thr - 1e-4)
+  float p_gt;         // a probability above this is above the threshold for sure (thr + 1e-4)
+  float thr_lo;       // shortlist trigger: e_k > thr_lo * S (thr_lo slightly under thr)
+  float p_clear;      // rescale factor under which everything seen before a new minimum is out
+  int mid_dy, mid_blk, mid_r, middle;  // zero-flow entry (dy, dx-block, column in block; 1-based index)
+  int cy, cx;                          // ceil(maxh/2), ceil(maxw/2)
   int h_img, w_img, hoff, woff;
   long long *index;
   float *min_ssd, *pmax, *flow_full;
   long long *index_thr;
   float *score_thr, *soft_yx;
   unsigned long long *n_untouched;
-  float *cand_v;  // [grid][256][P][kNC]
-  int *cand_k;
+  // thresholded extraction (extractOutput on the probabilities), see ExtractEpi::tile_end
+  int nwords;           // 32-bit words of the per-pixel (dy, dx-block) shortlist bitmap
+  int *todo;            // pixels that need the exact pass over their shortlist
+  unsigned *todo_mask;  // [todo slot][nwords]
+  unsigned *ntodo;
+  float *vmin, *vinv;   // per-pixel min and 1/sum for the exact pass
 };
 
+// Per-thread state of the fused reduction: for each of the thread's kP pixels the running
+// minimum (and its index), the softmax denominator and -- when SOFT -- the two first
+// moments, all relative to the running minimum (flash-style rescaling when it moves).
+// Shared memory per pixel: the shortlist bitmap [nwords] and the SSD of the zero-flow entry.
+template <bool SOFT>
+struct ExtractEpi {
+  const ExtractParams &P;
+  float m[kP], v2[kP], S[kP], sx[kP], sy[kP];  // v2: second smallest SSD among shortlisted entries
+  int idx[kP];
+  unsigned *mask;  // [nwords][kP][kCThreads] words, this thread's column
+  float *vmid;     // [kP][kCThreads]
+
+  __device__ ExtractEpi(const ExtractParams &p, unsigned *smem_extra)
+      : P(p), mask(smem_extra + threadIdx.x) {
+    vmid = reinterpret_cast<float *>(smem_extra + (size_t)p.nwords * kP * kCThreads) + threadIdx.x;
+  }
+
+  __device__ __forceinline__ void tile_begin(int, int, int) {
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      m[p] = v2[p] = __int_as_float(0x7f800000);
+      S[p] = sx[p] = sy[p] = 0.0f;
+      idx[p] = 1;
+      vmid[p * kCThreads] = 0.0f;
+    }
+    for (int w = 0; w < P.nwords * kP; ++w) mask[w * kCThreads] = 0u;
+  }
+
+  // a new running minimum v at 1-based index k for pixel p (strict <: the first occurrence
+  // wins, like TH max): rescale what was accumulated relative to the old one
+  __device__ __forceinline__ void new_min(int p, float v, int k) {
+    const float sc = ex2_approx((v - m[p]) * kLog2e);  // old m = +inf -> 0
+    S[p] *= sc;
+    if (SOFT) {
+      sx[p] *= sc;
+      sy[p] *= sc;
+    }
+    if (P.nwords) {
+      if (sc < P.p_clear) {
+        // the old minimum (and everything before it) is now below the threshold for good
+        for (int w = 0; w < P.nwords; ++w) mask[(w * kP + p) * kCThreads] = 0u;
+        v2[p] = __int_as_float(0x7f800000);
+      } else {
+        v2[p] = fminf(v2[p], m[p]);  // the old minimum is now a runner-up
+      }
+    }
+    m[p] = v;
+    idx[p] = k;
+  }
+
+  __device__ __forceinline__ void block(float (&acc)[kP][kR], int dy, int blk, int rvalid) {
+    const float inf = __int_as_float(0x7f800000);
+    if (rvalid < kR) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+#pragma unroll
+        for (int r = 0; r < kR; ++r)
+          if (r >= rvalid) acc[p][r] = inf;
+    }
+    // zero-flow entry, for the tie rule (warp-uniform branch, once per sweep)
+    if (dy == P.mid_dy && blk == P.mid_blk) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+#pragma unroll
+        for (int r = 0; r < kR; ++r)
+          if (r == P.mid_r) vmid[p * kCThreads] = acc[p][r];
+    }
+    float bm[kP];
+    bool any = false, nm[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      nm[p] = false;
+      bm[p] = acc[p][0];
+#pragma unroll
+      for (int r = 1; r < kR; ++r) bm[p] = fminf(bm[p], acc[p][r]);
+      any |= bm[p] < m[p];
+    }
+    if (any) {  // some pixel of this thread has a new running minimum in this block
+      const int kbase = (dy * P.g.maxw + blk * kR) + 1;  // 1-based index of r = 0
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+        if (bm[p] < m[p]) {
+          int rb = 0;
+#pragma unroll
+          for (int r = kR - 1; r >= 0; --r)
+            if (acc[p][r] == bm[p]) rb = r;
+          new_min(p, bm[p], kbase + rb);
+          nm[p] = true;
+        }
+    }
+    const float rowf = (float)(dy + 1), colf = (float)(blk * kR);
+    bool cand = false;
+    float eb[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const float mL = m[p] * kLog2e;
+      float ex = 0.0f;
+      eb[p] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < kR; ++r) {
+        const float e = ex2_approx(fmaf(acc[p][r], -kLog2e, mL));
+        eb[p] += e;
+        if (SOFT) ex = fmaf(e, (float)(r + 1), ex);
+      }
+      S[p] += eb[p];
+      if (SOFT) {
+        sx[p] += fmaf(eb[p], colf, ex);
+        sy[p] = fmaf(eb[p], rowf, sy[p]);
+      }
+      // thresholded extraction: p_k(final) <= e_k / S(now), so an entry of this block can
+      // end above the threshold only if the block's largest e exceeds thr * S
+      if (P.nwords) cand |= ex2_approx(fmaf(bm[p], -kLog2e, mL)) > P.thr_lo * S[p];
+    }
+    if (cand) {
+      const int bit = dy * P.g.bs.per_row() + blk;
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+        if (ex2_approx((m[p] - bm[p]) * kLog2e) > P.thr_lo * S[p]) {
+          mask[((bit >> 5) * kP + p) * kCThreads] |= 1u << (bit & 31);
+          // every entry that can still end above the threshold passes through here, so the
+          // second smallest SSD seen here bounds the second largest probability (tile_end)
+          float lo = m[p], hi = v2[p];
+#pragma unroll
+          for (int r = 0; r < kR; ++r) {
+            const float v = acc[p][r];
+            hi = fminf(hi, fmaxf(lo, v));
+            lo = fminf(lo, v);
+          }
+          // lo started at the running minimum so that a tie with it is recorded; when the
+          // minimum was set by this very block it must be counted once, not twice
+          v2[p] = nm[p] ? second_smallest(acc[p], v2[p]) : hi;
+        }
+    }
+  }
+
+  // second smallest of {acc[0..8)} and v2_old, where the smallest of acc is the running minimum
+  __device__ __forceinline__ static float second_smallest(const float (&v)[kR], float v2_old) {
+    float lo = __int_as_float(0x7f800000), hi = v2_old;
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      hi = fminf(hi, fmaxf(lo, v[r]));
+      lo = fminf(lo, v[r]);
+    }
+    return hi;
+  }
+
+  __device__ __forceinline__ void column(float (&acc)[kP], int dy, int blk) {
+    if (dy == P.mid_dy && blk == P.mid_blk) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p) vmid[p * kCThreads] = acc[p];
+    }
+    const int k = dy * P.g.maxw + blk * kR + 1;
+    const int bit = dy * P.g.bs.per_row() + blk;
+    const float rowf = (float)(dy + 1), colf = (float)(blk * kR + 1);
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const bool isnew = acc[p] < m[p];
+      if (isnew) new_min(p, acc[p], k);
+      const float e = ex2_approx((m[p] - acc[p]) * kLog2e);
+      S[p] += e;
+      if (SOFT) {
+        sx[p] = fmaf(e, colf, sx[p]);
+        sy[p] = fmaf(e, rowf, sy[p]);
+      }
+      if (P.nwords && e > P.thr_lo * S[p]) {
+        mask[((bit >> 5) * kP + p) * kCThreads] |= 1u << (bit & 31);
+        if (!isnew) v2[p] = fminf(v2[p], acc[p]);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void tile_end(int n, int y, int x0) {
+    const SweepGeom &g = P.g;
+    if (y >= g.H1) return;
+    unsigned untouched = 0;
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const int x = x0 + p;
+      if (x >= g.W1) continue;
+      const size_t o = ((size_t)n * g.H1 + y) * g.W1 + x;
+      const float inv = 1.0f / S[p];
+      int win = idx[p];
+      if ((P.flags & DM_FLAG_TIE_MIDDLE) && win != P.middle) {
+        const float emid = expf(m[p] - vmid[p * kCThreads]);
+        if (emid * inv == inv) win = P.middle;  // p[middle] == max p (opticalflow_model.lua:157-159)
+      }
+      if (P.index) P.index[o] = win;
+      if (P.min_ssd) P.min_ssd[o] = m[p];
+      if (P.pmax) P.pmax[o] = inv;
+      if (SOFT && P.soft_yx) {
+        const size_t plane = (size_t)g.H1 * g.W1;
+        const size_t so = (size_t)n * 2 * plane + (size_t)y * g.W1 + x;
+        P.soft_yx[so] = sy[p] * inv;
+        P.soft_yx[so + plane] = sx[p] * inv;
+      }
+      if (P.flow_full) {
+        const int row = (win - 1) / g.maxw + 1, col = (win - 1) % g.maxw + 1;
+        const size_t plane = (size_t)P.h_img * P.w_img;
+        const size_t fo = (size_t)n * 2 * plane + (size_t)(y + P.hoff) * P.w_img + (x + P.woff);
+        P.flow_full[fo] = (float)(row - P.cy);
+        P.flow_full[fo + plane] = (float)(col - P.cx);
+      }
+      if (P.todo) {
+        // extractOutput(prob, thr) (extract_output.cpp:63-155).  pmax < thr: nothing qualifies,
+        // the pixel stays untouched.  pmax > thr and the second largest probability
+        // exp(m - v2)/S < thr: the list is {pmax}, ret = its position, score = M * pmax (prefix
+        // sums of {pmax,0,..}).  Anything within 1e-4 of those borders, and every pixel with two
+        // or more entries above the threshold, goes to the exact per-pixel pass, which re-scores
+        // only the (dy, dx-block)s on the pixel's shortlist.
+        long long ret = 0;
+        float score = 0.0f;
+        const float p2 = expf(m[p] - v2[p]) * inv;
+        if (inv > P.p_gt && p2 < P.p_none) {
+          ret = idx[p];
+          score = (float)((double)P.M * (double)inv);
+        } else if (inv < P.p_none) {
+          ++untouched;
+        } else {
+          const unsigned slot = atomicAdd(P.ntodo, 1u);
+          P.todo[slot] = (int)o;
+          for (int w = 0; w < P.nwords; ++w)
+            P.todo_mask[(size_t)slot * P.nwords + w] = mask[(w * kP + p) * kCThreads];
+          P.vmin[o] = m[p];
+          P.vinv[o] = inv;
+        }
+        if (P.index_thr) P.index_thr[o] = ret;
+        if (P.score_thr) P.score_thr[o] = score;
+      }
+    }
+    if (P.n_untouched && untouched) atomicAdd(P.n_untouched + n, (unsigned long long)untouched);
+  }
+};
+
+template <int CT, bool EXACT, bool SOFT>
+__global__ void __launch_bounds__(kThreads, 1)
+match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const ExtractParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *ring = reinterpret_cast<float *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kNSlot * P.g.slab_floats);
+  unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
+  ExtractEpi<SOFT> epi(P, extra);
+  run_sweep<CT, EXACT>(&tmap, P.g, ring, full, epi);
+}
+
+// ---------------------------------------------------------------- exact threshold pass
 // sorting networks of the reference (extract_output.cpp:27-33, :35-61), same order
 __device__ __constant__ unsigned char kNet4[5][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}, {1, 2}};
 __device__ __constant__ unsigned char kNet8[19][2] = {
@@ -64,187 +314,91 @@ __device__ inline void net_sort_score(float *val, float *pos, int M, long long *
   *score = (float)acc;
 }
 
-struct ExtractEpi {
-  const ExtractParams &P;
-  float m[kP], mL[kP], thr[kP], S[kP], sx[kP], sy[kP], vmid[kP];
-  int idx[kP];
-  int cnt[kP];
-  float *cv;
-  int *ck;
-
-  __device__ explicit ExtractEpi(const ExtractParams &p) : P(p) {
-    const size_t base = ((size_t)blockIdx.x * kThreads + threadIdx.x) * kP * kNC;
-    cv = p.cand_v + base;
-    ck = p.cand_k + base;
-  }
-
-  __device__ __forceinline__ void tile_begin(int, int, int) {
-#pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      m[p] = __int_as_float(0x7f800000);
-      mL[p] = m[p];
-      thr[p] = m[p];
-      S[p] = sx[p] = sy[p] = 0.0f;
-      vmid[p] = 0.0f;
-      idx[p] = 1;
-      cnt[p] = 0;
-    }
-  }
-
-  // keep the kNC smallest values seen, in scan order
-  __device__ __noinline__ static float cand_insert(float *cv, int *ck, int *cnt, float v, int k) {
-    int n = *cnt;
-    if (n == kNC) {
-      int jmax = 0;
-      float vmax = cv[0];
-      for (int j = 1; j < kNC; ++j)
-        if (cv[j] >= vmax) {  // >= : among equals evict the latest
-          vmax = cv[j];
-          jmax = j;
-        }
-      if (!(v < vmax)) return vmax;
-      for (int j = jmax; j + 1 < kNC; ++j) {
-        cv[j] = cv[j + 1];
-        ck[j] = ck[j + 1];
-      }
-      n = kNC - 1;
-    }
-    cv[n] = v;
-    ck[n] = k;
-    *cnt = ++n;
-    if (n < kNC) return __int_as_float(0x7f800000);
-    float vmax = cv[0];
-    for (int j = 1; j < kNC; ++j) vmax = fmaxf(vmax, cv[j]);
-    return vmax;
-  }
-
-  template <int R>
-  __device__ __forceinline__ void block(float (&acc)[kP][R], int dy, int dxb, int rvalid) {
-    const float inf = __int_as_float(0x7f800000);
-    if (rvalid < R) {
-#pragma unroll
-      for (int p = 0; p < kP; ++p)
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (r >= rvalid) acc[p][r] = inf;
-    }
-    // zero-flow entry, for the tie rule (warp-uniform branch)
-    if (dy == P.mid_dy && P.mid_dx >= dxb && P.mid_dx < dxb + R) {
-      const int rr = P.mid_dx - dxb;
-#pragma unroll
-      for (int p = 0; p < kP; ++p)
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (r == rr) vmid[p] = acc[p][r];
-    }
-    const int kbase = dy * P.g.maxw + dxb + 1;  // 1-based index of r = 0
-    const float rowf = (float)(dy + 1), colf = (float)dxb;
-#pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      float bm = acc[p][0];
-#pragma unroll
-      for (int r = 1; r < R; ++r) bm = fminf(bm, acc[p][r]);
-      if (bm < thr[p]) {
-        // rare path: a new minimum and/or a candidate for the thresholded extraction
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float v = acc[p][r];
-          const bool cand = P.cand_margin > 0.0f;
-          if (v < m[p]) {
-            const float sc = ex2_approx((v - m[p]) * kLog2e);  // m = +inf -> 0
-            S[p] *= sc;
-            sx[p] *= sc;
-            sy[p] *= sc;
-            m[p] = v;
-            mL[p] = v * kLog2e;
-            idx[p] = kbase + r;
-            // invariant: thr = min(m + margin, largest kept candidate) >= m
-            thr[p] = cand ? fminf(thr[p], v + P.cand_margin) : v;
-          }
-          if (cand && v < thr[p]) {
-            const float lmax = cand_insert(cv + p * kNC, ck + p * kNC, &cnt[p], v, kbase + r);
-            thr[p] = fminf(m[p] + P.cand_margin, lmax);
-          }
-        }
-      }
-      float eb = 0.0f, ex = 0.0f;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float e = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p]));
-        eb += e;
-        ex = fmaf(e, (float)(r + 1), ex);
-      }
-      S[p] += eb;
-      sx[p] += fmaf(eb, colf, ex);
-      sy[p] = fmaf(eb, rowf, sy[p]);
-    }
-  }
-
-  __device__ __forceinline__ void tile_end(int n, int y, int x0) {
-    const SweepGeom &g = P.g;
-    if (y >= g.H1) return;
-    unsigned untouched = 0;
-#pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      const int x = x0 + p;
-      if (x >= g.W1) continue;
-      const size_t o = ((size_t)n * g.H1 + y) * g.W1 + x;
-      const float inv = 1.0f / S[p];
-      int win = idx[p];
-      if ((P.flags & DM_FLAG_TIE_MIDDLE) && win != P.middle) {
-        const float emid = expf(m[p] - vmid[p]);
-        if (emid * inv == inv) win = P.middle;  // p[middle] == max p (opticalflow_model.lua:157-159)
-      }
-      if (P.index) P.index[o] = win;
-      if (P.min_ssd) P.min_ssd[o] = m[p];
-      if (P.pmax) P.pmax[o] = inv;
-      if (P.soft_yx) {
-        const size_t plane = (size_t)g.H1 * g.W1;
-        const size_t so = (size_t)n * 2 * plane + (size_t)y * g.W1 + x;
-        P.soft_yx[so] = sy[p] * inv;
-        P.soft_yx[so + plane] = sx[p] * inv;
-      }
-      if (P.flow_full) {
-        const int row = (win - 1) / g.maxw + 1, col = (win - 1) % g.maxw + 1;
-        const size_t plane = (size_t)P.h_img * P.w_img;
-        const size_t fo = (size_t)n * 2 * plane + (size_t)(y + P.hoff) * P.w_img + (x + P.woff);
-        P.flow_full[fo] = (float)(row - P.cy);
-        P.flow_full[fo + plane] = (float)(col - P.cx);
-      }
-      if (P.index_thr || P.score_thr || P.n_untouched) {
-        float val[8], pos[8];
-        for (int j = 0; j < 8; ++j) val[j] = pos[j] = 0.0f;
-        int got = 0;
-        for (int j = 0; j < cnt[p] && got < P.M; ++j) {
-          const float pk = expf(m[p] - cv[p * kNC + j]) * inv;
-          if ((double)pk > P.thr) {
-            val[got] = pk;
-            pos[got] = (float)ck[p * kNC + j];
-            ++got;
-          }
-        }
-        long long ret = 0;
-        float score = 0.0f;
-        if (got > 0)
-          net_sort_score(val, pos, P.M, &ret, &score);
-        else
-          ++untouched;
-        if (P.index_thr) P.index_thr[o] = ret;
-        if (P.score_thr) P.score_thr[o] = score;
-      }
-    }
-    if (P.n_untouched && untouched) atomicAdd(P.n_untouched + n, (unsigned long long)untouched);
-  }
+struct ThresholdPass {
+  const float *in1, *in2;
+  long long s1n, s1c, s1y, s2n, s2c, s2y;
+  int N, C, H1, W1, maxh, maxw, nwords, M, exact;
+  BlockSchedule bs;
+  double thr;
+  const int *todo;
+  const unsigned *todo_mask, *ntodo;
+  const float *vmin, *vinv;
+  long long *index_thr;
+  float *score_thr;
+  unsigned long long *n_untouched;
 };
 
-template <int CT, bool EXACT>
-__global__ void __launch_bounds__(kThreads, 1)
-match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const ExtractParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float *ring = reinterpret_cast<float *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kNSlot * P.g.C * P.g.WB);
-  ExtractEpi epi(P);
-  run_sweep<CT, EXACT>(&tmap, P.g, ring, full, epi);
+// Exact extractOutput for the pixels the sweep could not decide: one warp per pixel walks the
+// pixel's shortlist of (dy, dx-block)s in scan order, recomputes those SSDs with the same
+// arithmetic as the sweep (all channel loads of a block issued before the first use, so a
+// block costs one memory latency), and applies extract_output.cpp:63-155 literally.
+__global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPass T) {
+  const int lane = threadIdx.x & 31;
+  const unsigned n = *T.ntodo;
+  const int per_row = T.bs.per_row();
+  for (unsigned e = blockIdx.x * 4 + (threadIdx.x >> 5); e < n; e += gridDim.x * 4) {
+    const long long px = T.todo[e];
+    const int x = (int)(px % T.W1), y = (int)((px / T.W1) % T.H1);
+    const int pn = (int)(px / ((long long)T.W1 * T.H1));
+    const float *a = T.in1 + pn * T.s1n + y * T.s1y + x;
+    const float *b0 = T.in2 + pn * T.s2n + y * T.s2y + x;
+    const float m = T.vmin[px], inv = T.vinv[px];
+    float av[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) av[c] = c < T.C ? __ldg(a + c * T.s1c) : 0.0f;
+    float val[8], pos[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) val[j] = pos[j] = 0.0f;
+    int got = 0;
+    for (int w = 0; w < T.nwords && got < T.M; ++w) {
+      unsigned bits = T.todo_mask[(size_t)e * T.nwords + w];
+      while (bits && got < T.M) {
+        const int id = w * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int dy = id / per_row, blk = id - dy * per_row;
+        const int dxb = blk * kR;
+        const int width = blk >= T.bs.n8 ? 1 : (blk == T.bs.n8 - 1 ? T.bs.last_valid : kR);
+        float pk = 0.0f;
+        if (lane < width) {
+          const float *b = b0 + dy * T.s2y + dxb + lane;
+          float bv[kMaxC];
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c) bv[c] = c < T.C ? __ldg(b + c * T.s2c) : 0.0f;
+          float acc = 0.0f;
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c)
+            if (c < T.C) {
+              const float d = av[c] - bv[c];
+              acc = T.exact ? __fadd_rn(acc, __fmul_rn(d, d)) : fmaf(d, d, acc);
+            }
+          pk = expf(m - acc) * inv;
+        }
+        unsigned hit = __ballot_sync(0xffffffffu, lane < width && (double)pk > T.thr);
+        while (hit && got < T.M) {
+          const int src = __ffs(hit) - 1;
+          hit &= hit - 1;
+          const float pv = __shfl_sync(0xffffffffu, pk, src);
+          const float pp = (float)(dy * T.maxw + dxb + src + 1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j == got) {
+              val[j] = pv;
+              pos[j] = pp;
+            }
+          ++got;
+        }
+      }
+    }
+    if (lane != 0) continue;
+    long long ret = 0;
+    float score = 0.0f;
+    if (got > 0)
+      net_sort_score(val, pos, T.M, &ret, &score);
+    else if (T.n_untouched)
+      atomicAdd(T.n_untouched + pn, 1ull);
+    if (T.index_thr) T.index_thr[px] = ret;
+    if (T.score_thr) T.score_thr[px] = score;
+  }
 }
 
 // ---------------------------------------------------------------- volume epilogue
@@ -260,20 +414,19 @@ constexpr int kStgStride = kTW + 4;  // floats per staged displacement row (bank
 
 struct VolumeEpi {
   const VolumeParams &P;
-  float *stg;  // this warp's staging area: [kRT][kStgStride]
+  float *stg;  // this warp's staging area: [kR][kStgStride]
   float mL[kP], inv[kP];
   size_t obase;  // output offset of (n, y, tile x)
   int npx;       // valid pixels of this warp's row in the tile
-  bool rowok;
 
   __device__ VolumeEpi(const VolumeParams &p, float *stg_all)
-      : P(p), stg(stg_all + (threadIdx.x >> 5) * (kRT * kStgStride)) {}
+      : P(p), stg(stg_all + (threadIdx.x >> 5) * (kR * kStgStride)) {}
 
   __device__ __forceinline__ void tile_begin(int n, int y, int x0) {
     const SweepGeom &g = P.g;
     const int lane = threadIdx.x & 31;
     const int xt = x0 - lane * kP;
-    rowok = y < g.H1;
+    const bool rowok = y < g.H1;
     npx = rowok ? min(kTW, g.W1 - xt) : 0;
     obase = (((size_t)n * g.H1 + (rowok ? y : 0)) * g.W1 + xt) * (size_t)(g.maxh * g.maxw);
 #pragma unroll
@@ -288,30 +441,44 @@ struct VolumeEpi {
     }
   }
 
-  template <int R>
-  __device__ __forceinline__ void block(float (&acc)[kP][R], int dy, int dxb, int rvalid) {
+  // stage `nr` displacement rows of 128 pixels, then write rvalid consecutive floats per pixel
+  __device__ __forceinline__ void flush(int dy, int dxb, int rvalid) {
     const int lane = threadIdx.x & 31;
     const int K = P.g.maxh * P.g.maxw;
-    if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
-#pragma unroll
-      for (int p = 0; p < kP; ++p)
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          acc[p][r] = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p])) * inv[p];
-    }
     __syncwarp();
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      *reinterpret_cast<float4 *>(stg + r * kStgStride + lane * kP) =
-          make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
-    __syncwarp();
-    // each pixel owns `rvalid` consecutive floats of the output for this (dy, dx-block)
     const int total = npx * rvalid;
     float *dst = P.out + obase + (size_t)dy * P.g.maxw + dxb;
     for (int i = lane; i < total; i += 32) {
       const int px = i / rvalid, r = i - px * rvalid;
       dst[(size_t)px * K + r] = stg[r * kStgStride + px];
     }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void block(float (&acc)[kP][kR], int dy, int blk, int rvalid) {
+    const int lane = threadIdx.x & 31;
+    if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+#pragma unroll
+        for (int r = 0; r < kR; ++r)
+          acc[p][r] = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p])) * inv[p];
+    }
+#pragma unroll
+    for (int r = 0; r < kR; ++r)
+      *reinterpret_cast<float4 *>(stg + r * kStgStride + lane * kP) =
+          make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
+    flush(dy, blk * kR, rvalid);
+  }
+
+  __device__ __forceinline__ void column(float (&acc)[kP], int dy, int blk) {
+    const int lane = threadIdx.x & 31;
+    if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p) acc[p] = ex2_approx(fmaf(acc[p], -kLog2e, mL[p])) * inv[p];
+    }
+    *reinterpret_cast<float4 *>(stg + lane * kP) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    flush(dy, blk * kR, 1);
   }
 
   __device__ __forceinline__ void tile_end(int, int, int) {}
@@ -322,14 +489,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 match_volume_kernel(const __grid_constant__ CUtensorMap tmap, const VolumeParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ring = reinterpret_cast<float *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kNSlot * P.g.C * P.g.WB);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kNSlot * P.g.slab_floats);
   float *stg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
   VolumeEpi epi(P, stg);
   run_sweep<CT, EXACT>(&tmap, P.g, ring, full, epi);
 }
 
 // ---------------------------------------------------------------- host side
-static size_t ring_bytes(int C, int WB) { return (size_t)kNSlot * C * WB * sizeof(float); }
+static size_t ring_bytes(const SweepGeom &g) { return (size_t)kNSlot * g.slab_floats * sizeof(float); }
 
 struct Prepared {
   SweepGeom g;
@@ -337,6 +504,8 @@ struct Prepared {
   int CT;
   const float *in1_dev;
   const float *in2_dev;
+  long long s2n, s2c, s2y;  // strides of in2_dev (elements)
+  int Cin;
 };
 
 // Stage inputs (host -> device, or repack device views TMA cannot describe) and
@@ -362,7 +531,7 @@ static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, Prepared *
   g.W2 = in->w2;
   g.maxh = maxh;
   g.maxw = maxw;
-  block_schedule(maxw, &g.nfull, &g.tailw);
+  g.bs = block_schedule(maxw);
   g.WB = slab_width(maxw);
   g.tiles_x = (g.W1 + kTW - 1) / kTW;
   g.tiles_y = (g.H1 + kTH - 1) / kTH;
@@ -422,12 +591,18 @@ static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, Prepared *
   }
   out->in1_dev = d1;
   out->in2_dev = d2;
+  out->s2n = s2n;
+  out->s2c = s2c;
+  out->s2y = s2y;
+  out->Cin = g.C;
   const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, (uint64_t)g.C, (uint64_t)g.N};
   const uint64_t strides[3] = {(uint64_t)s2y * 4, (uint64_t)s2c * 4, (uint64_t)s2n * 4};
   const uint32_t box[4] = {(uint32_t)g.WB, 1u, (uint32_t)out->CT, 1u};
   DM_CHECK(encode_tensor_map_4d(&out->tmap, d2, dims, strides, box));
-  // the kernels address the ring with the box's channel count
+  // the kernels address the ring with the box's channel count; slots start on 128-byte
+  // boundaries (TMA destination alignment)
   g.C = out->CT;
+  g.slab_floats = (g.C * g.WB + 31) & ~31;
   return DM_OK;
 }
 
@@ -435,6 +610,15 @@ int generic_match_extract(Call &call, const dm_pair *in, int maxh, int maxw, uns
                           double thr, int h_img, int w_img, const dm_extract_out *out);
 int generic_match_volume(Call &call, const dm_pair *in, int maxh, int maxw, int mode, bool exact,
                          float *out);
+static const void *pick_extract(int CT, bool exact, bool soft) {
+#define DM_PICK(ct)                                                                             \
+  (exact ? (soft ? (const void *)match_extract_kernel<ct, true, true>                            \
+                 : (const void *)match_extract_kernel<ct, true, false>)                          \
+         : (soft ? (const void *)match_extract_kernel<ct, false, true>                           \
+                 : (const void *)match_extract_kernel<ct, false, false>))
+  return CT == 4 ? DM_PICK(4) : (CT == 10 ? DM_PICK(10) : DM_PICK(16));
+#undef DM_PICK
+}
 
 static int grid_for(dm_ctx *ctx, const void *kernel, size_t smem, int ntiles) {
   int per_sm = 1;
@@ -478,15 +662,19 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
   ExtractParams P;
   P.g = g;
   P.flags = flags;
-  P.thr = prob_threshold;
-  // v_k < min + ln(1/thr) is necessary for p_k > thr; <= 0 switches candidates off
-  P.cand_margin = want_thr ? (float)(log(1.0 / prob_threshold) + 1e-3) : 0.0f;
   P.M = prob_threshold < 0.2 ? 8 : 4;
+  // decide in the sweep only when it is safe by a margin; the rest goes to the exact pass
+  P.p_none = (float)(prob_threshold - 1e-4);
+  P.p_gt = (float)(prob_threshold + 1e-4);
+  P.thr_lo = (float)(prob_threshold * 0.999);
+  P.p_clear = (float)(prob_threshold * 0.99);
   P.cy = (maxh + 1) / 2;
   P.cx = (maxw + 1) / 2;
   P.mid_dy = P.cy - 1;
-  P.mid_dx = P.cx - 1;
-  P.middle = P.mid_dy * maxw + P.mid_dx + 1;
+  P.mid_blk = (P.cx - 1) / kR;
+  P.mid_r = (P.cx - 1) % kR;
+  if (P.mid_blk >= g.bs.n8) P.mid_r = 0;  // the zero-flow column is the trailing single column
+  P.middle = P.mid_dy * maxw + P.cx;
   P.h_img = h_img;
   P.w_img = w_img;
   P.hoff = (h_img - g.H1) / 2;
@@ -516,26 +704,50 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
   if (P.flow_full)
     DM_CUDA(cudaMemsetAsync(P.flow_full, 0, (size_t)g.N * 2 * h_img * w_img * 4, ctx->stream));
 
-  const size_t smem = ring_bytes(g.C, g.WB) + kBarBytes;
+  P.nwords = 0;
+  P.todo = nullptr;
+  P.todo_mask = nullptr;
+  P.ntodo = nullptr;
+  P.vmin = P.vinv = nullptr;
+  if (want_thr) {
+    // one shortlist bit per (dy, dx-block); S >= 1 so p_k > thr needs v_k < min + ln(1/thr)
+    P.nwords = (maxh * g.bs.per_row() + 31) / 32;
+    void *scratch = nullptr;
+    DM_CHECK(call.alloc(&scratch, 256 + npx * sizeof(int) * (1 + (size_t)P.nwords) + npx * 8));
+    P.ntodo = static_cast<unsigned *>(scratch);
+    P.todo = static_cast<int *>(scratch) + 64;
+    P.todo_mask = reinterpret_cast<unsigned *>(P.todo + npx);
+    P.vmin = reinterpret_cast<float *>(P.todo_mask + npx * P.nwords);
+    P.vinv = P.vmin + npx;
+    DM_CUDA(cudaMemsetAsync(P.ntodo, 0, sizeof(unsigned), ctx->stream));
+  }
+  const size_t smem = ring_bytes(g) + kBarBytes + (size_t)(P.nwords + 1) * kCThreads * kP * sizeof(unsigned);
   DM_REQUIRE(smem <= ctx->smem_optin, "window %dx%d with %d channels needs %zu bytes of shared memory",
              maxh, maxw, g.C, smem);
   const bool exact = flags & DM_FLAG_EXACT_SSD;
   const void *kfn = nullptr;
-#define DM_PICK(ct)                                                                   \
-  (exact ? (const void *)match_extract_kernel<ct, true> : (const void *)match_extract_kernel<ct, false>)
-  kfn = pr.CT == 4 ? DM_PICK(4) : (pr.CT == 10 ? DM_PICK(10) : DM_PICK(16));
-#undef DM_PICK
+  kfn = pick_extract(pr.CT, exact, P.soft_yx != nullptr);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = grid_for(ctx, kfn, smem, g.ntiles);
-  void *scratch = nullptr;
-  DM_CHECK(call.alloc(&scratch, (size_t)grid * kThreads * kP * kNC * 8));
-  P.cand_v = static_cast<float *>(scratch);
-  P.cand_k = reinterpret_cast<int *>(P.cand_v + (size_t)grid * kThreads * kP * kNC);
   void *args[] = {(void *)&pr.tmap, (void *)&P};
   prof_begin(ctx);
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
   prof_end(ctx);
   count_launch(ctx);
+  if (want_thr) {
+    ThresholdPass T;
+    T.in1 = g.in1; T.s1n = g.s1n; T.s1c = g.s1c; T.s1y = g.s1y;
+    T.in2 = pr.in2_dev; T.s2n = pr.s2n; T.s2c = pr.s2c; T.s2y = pr.s2y;
+    T.N = g.N; T.C = pr.Cin; T.H1 = g.H1; T.W1 = g.W1; T.maxh = maxh; T.maxw = maxw;
+    T.bs = g.bs; T.nwords = P.nwords; T.M = P.M; T.exact = exact ? 1 : 0;
+    T.thr = prob_threshold;
+    T.todo = P.todo; T.todo_mask = P.todo_mask; T.ntodo = P.ntodo;
+    T.vmin = P.vmin; T.vinv = P.vinv;
+    T.index_thr = P.index_thr; T.score_thr = P.score_thr; T.n_untouched = P.n_untouched;
+    threshold_exact_kernel<<<ctx->num_sms * 12, 128, 0, ctx->stream>>>(T);
+    DM_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  }
   return call.finish();
 }
 
@@ -550,28 +762,19 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
   memset(&P, 0, sizeof(P));
   P.g = g;
   P.flags = 0;
-  P.thr = 1.0;
-  P.cand_margin = 0.0f;
   P.M = 8;
   P.cy = (g.maxh + 1) / 2;
   P.cx = (g.maxw + 1) / 2;
   P.mid_dy = P.cy - 1;
-  P.mid_dx = P.cx - 1;
-  P.middle = P.mid_dy * g.maxw + P.mid_dx + 1;
+  P.mid_blk = (P.cx - 1) / kR;
+  P.mid_r = (P.cx - 1) % kR;
+  P.middle = P.mid_dy * g.maxw + P.cx;
   P.min_ssd = vmin;
   P.pmax = vinv;
-  const size_t smem = ring_bytes(g.C, g.WB) + kBarBytes;
-  const void *kfn;
-#define DM_PICK(ct)                                                                   \
-  (exact ? (const void *)match_extract_kernel<ct, true> : (const void *)match_extract_kernel<ct, false>)
-  kfn = pr.CT == 4 ? DM_PICK(4) : (pr.CT == 10 ? DM_PICK(10) : DM_PICK(16));
-#undef DM_PICK
+  const size_t smem = ring_bytes(g) + kBarBytes + (size_t)kCThreads * kP * sizeof(unsigned);
+  const void *kfn = pick_extract(pr.CT, exact, false);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = grid_for(ctx, kfn, smem, g.ntiles);
-  void *scratch = nullptr;
-  DM_CHECK(call.alloc(&scratch, (size_t)grid * kThreads * kP * kNC * 8));
-  P.cand_v = static_cast<float *>(scratch);
-  P.cand_k = reinterpret_cast<int *>(P.cand_v + (size_t)grid * kThreads * kP * kNC);
   void *args[] = {(void *)&pr.tmap, (void *)&P};
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
   count_launch(ctx);
@@ -614,8 +817,8 @@ extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int max
     P.vmin = vmin;
     P.vinv = vinv;
   }
-  const size_t smem = ring_bytes(g.C, g.WB) + kBarBytes +
-                      (size_t)kWarps * kRT * kStgStride * sizeof(float);
+  const size_t smem = ring_bytes(g) + kBarBytes +
+                      (size_t)kWarps * kR * kStgStride * sizeof(float);
   DM_REQUIRE(smem <= ctx->smem_optin, "window %dx%d with %d channels needs %zu bytes of shared memory",
              maxh, maxw, g.C, smem);
 #define DM_PICKV(ct)                                                                  \

@@ -24,6 +24,7 @@ struct GenericParams {
   float *score_thr, *soft_yx;
   unsigned long long *n_untouched;
   float *radial_flow;  // argmin - 1 as float
+
   // volume
   int mode;
   float *vol;

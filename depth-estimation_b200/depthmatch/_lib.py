@@ -45,6 +45,7 @@ SIGNATURES = {
     "dm_destroy": (_I, [_P]),
     "dm_synchronize": (_I, [_P]),
     "dm_set_stream": (_I, [_P, _P]),
+    "dm_reset_stream": (_I, [_P]),
     "dm_get_stream": (_P, [_P]),
     "dm_host_alloc": (_I, [C.POINTER(_P), C.c_size_t]),
     "dm_host_free": (_I, [_P]),

@@ -43,7 +43,7 @@ class Context:
         check(self._lib.dm_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
-        self._stream = None
+        self._stream = "own"
 
     def close(self):
         if getattr(self, "_h", None):
@@ -75,9 +75,13 @@ class Context:
         return float(ms.value)
 
     def use_stream(self, cuda_stream):
-        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        """cuda_stream: integer cudaStream_t (torch.cuda.current_stream().cuda_stream; 0 is the
+        legacy default stream) or "own" for the context's private stream."""
         if cuda_stream != self._stream:
-            check(self._lib.dm_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+            if cuda_stream == "own":
+                check(self._lib.dm_reset_stream(self._h))
+            else:
+                check(self._lib.dm_set_stream(self._h, C.c_void_p(int(cuda_stream))))
             self._stream = cuda_stream
 
 

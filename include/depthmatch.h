@@ -51,8 +51,10 @@ const char *dm_last_error(void);
 int dm_create(int device, dm_ctx **ctx);
 int dm_destroy(dm_ctx *ctx);
 int dm_synchronize(dm_ctx *ctx);
-/* cudaStream_t as void*; NULL restores the context's own stream */
+/* run on the caller's stream (cudaStream_t as void*; NULL = CUDA's legacy default stream),
+ * or go back to the context's own non-blocking stream */
 int dm_set_stream(dm_ctx *ctx, void *cuda_stream);
+int dm_reset_stream(dm_ctx *ctx);
 void *dm_get_stream(dm_ctx *ctx);
 /* pinned host memory for callers that want full-speed staging (cudaHostAlloc) */
 int dm_host_alloc(void **ptr, size_t bytes);
