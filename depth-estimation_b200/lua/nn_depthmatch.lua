@@ -1,0 +1,145 @@
+-- nn_depthmatch.lua -- drop-in replacements, same class names and constructors as the
+-- reference, forward only (the hot path is inference; updateGradInput raises):
+--   nn.SpatialMatching(maxh, maxw, full_output)        nnx (opticalflow_model.lua:93)
+--   nn.SpatialRadialMatching(hWin)                      radial/radial_opticalflow_network.lua:32-34
+--   nn.CascadingAddTable(ratios, trainable, single_beta) CascadingAddTable.lua
+--   nn.OutputExtractor(maxh, maxw)                      OutputExtractor.lua
+--   nn.DenseMatch(geometry)                             fused SpatialMatching+Minus+SoftMax+extract
+--   extractoutput.extractOutput / extractOutputMarginalized   extract_output.cpp:357-366
+--   x2yxMulti2(geometry, x)                             opticalflow_model_multiscale.lua:72-81
+-- NOT EXECUTED in this repository (no Lua in the build image); see INTEGRATION.md.
+require 'torch'
+require 'nn'
+local ffi = require 'ffi'
+local dm = require 'depthmatch_ffi'
+local C, ctx = dm.C, dm.ctx
+
+local function nobackward(name)
+   return function() error(name .. ': backward is outside the inference hot path') end
+end
+
+-- ---------------------------------------------------------------- SpatialMatching
+local SpatialMatching, parent = torch.class('nn.SpatialMatching', 'nn.Module')
+function SpatialMatching:__init(maxh, maxw, full_output)
+   parent.__init(self)
+   assert(not full_output, 'full_output=true is never used by the reference')
+   self.maxh, self.maxw, self.full_output = maxh or 1, maxw or 1, false
+end
+function SpatialMatching:updateOutput(input)
+   local in1, in2 = input[1], input[2]
+   self.output:resize(in1:size(2), in1:size(3), self.maxh, self.maxw)
+   dm.check(C.dm_match_volume(ctx, dm.pair(in1, in2), self.maxh, self.maxw, dm.DM_VOLUME_SSD,
+                              torch.data(self.output)))
+   return self.output
+end
+SpatialMatching.updateGradInput = nobackward('nn.SpatialMatching')
+
+-- ---------------------------------------------------------------- SpatialRadialMatching
+local SpatialRadialMatching, rparent = torch.class('nn.SpatialRadialMatching', 'nn.Module')
+function SpatialRadialMatching:__init(hWin)
+   rparent.__init(self)
+   self.hWin = hWin
+end
+function SpatialRadialMatching:updateOutput(input)
+   local in1, in2 = input[1], input[2]
+   self.output:resize(in1:size(2), in1:size(3), self.hWin)
+   dm.check(C.dm_match_volume(ctx, dm.pair(in1, in2), self.hWin, 1, dm.DM_VOLUME_SSD,
+                              torch.data(self.output)))
+   return self.output
+end
+SpatialRadialMatching.updateGradInput = nobackward('nn.SpatialRadialMatching')
+
+-- ---------------------------------------------------------------- CascadingAddTable (forward)
+local CascadingAddTable, cparent = torch.class('nn.CascadingAddTable', 'nn.Module')
+function CascadingAddTable:__init(ratios, trainable, single_beta)
+   cparent.__init(self)
+   self.ratios = ratios
+   self.output = {}
+   for i = 1, #ratios do self.output[i] = torch.Tensor() end
+end
+function CascadingAddTable:updateOutput(input)
+   if #input ~= #self.ratios then
+      error('nn.CascadingAddTable: input and ratios must have the same size')
+   end
+   local n, rows, kh, kw = #input, input[1]:size(1), input[1]:size(2), input[1]:size(3)
+   local stacked = torch.Tensor(n, rows, kh, kw)
+   for i = 1, n do
+      if input[i]:nDimension() ~= 3 then
+         error('nn.CascadingAddTable: input must be a table of 3D-tensors (HxW) x Kh x Kw')
+      end
+      stacked[i]:copy(input[i])
+   end
+   local out = torch.Tensor(n, rows, kh, kw)
+   local rat = ffi.new('int[?]', n, self.ratios)
+   dm.check(C.dm_cascade_add(ctx, torch.data(stacked), rows, kh, kw, rat, n, torch.data(out)))
+   for i = 1, n do self.output[i] = out[i] end
+   return self.output
+end
+CascadingAddTable.updateGradInput = nobackward('nn.CascadingAddTable')
+function CascadingAddTable:parameters() return {}, {} end
+function CascadingAddTable:updateNormalizers() end
+
+-- ---------------------------------------------------------------- OutputExtractor
+local OutputExtractor = torch.class('nn.OutputExtractor', 'nn.Module')
+function OutputExtractor:__init(maxh, maxw)
+   self.maxh, self.maxw = maxh, maxw
+   self.output = nil
+end
+function OutputExtractor:updateOutput(input)
+   local inp = input:contiguous()
+   local h, w = inp:size(1), inp:size(2)
+   local x, y = torch.Tensor(h, w), torch.Tensor(h, w)
+   dm.check(C.dm_soft_mean(ctx, torch.data(inp), h * w, self.maxh, self.maxw, torch.data(y), torch.data(x)))
+   self.output = {x, y}
+   return self.output
+end
+OutputExtractor.updateGradInput = nobackward('nn.OutputExtractor')
+
+-- ---------------------------------------------------------------- DenseMatch (fused)
+-- forward({in1, in2}) returns the table processOutput would build (index, y, x, full, ...)
+local DenseMatch, dparent = torch.class('nn.DenseMatch', 'nn.Module')
+function DenseMatch:__init(geometry)
+   dparent.__init(self)
+   self.geometry = geometry
+end
+function DenseMatch:updateOutput(input)
+   local g, in1, in2 = self.geometry, input[1], input[2]
+   local h, w = in1:size(2), in1:size(3)
+   local ret = {index = torch.LongTensor(h, w), pmax = torch.Tensor(h, w),
+                index_thr = torch.LongTensor(h, w), scores = torch.Tensor(h, w),
+                soft = torch.Tensor(2, h, w), full = torch.Tensor(2, g.hImg, g.wImg)}
+   local o = ffi.new('dm_extract_out')
+   o.index, o.pmax = torch.data(ret.index), torch.data(ret.pmax)
+   o.index_thr, o.score_thr = torch.data(ret.index_thr), torch.data(ret.scores)
+   o.soft_yx, o.flow_full = torch.data(ret.soft), torch.data(ret.full)
+   dm.check(C.dm_match_extract(ctx, dm.pair(in1, in2), g.maxh, g.maxw, dm.DM_FLAG_TIE_MIDDLE, 0.11,
+                               g.hImg, g.wImg, o))
+   self.output = ret
+   return ret
+end
+DenseMatch.updateGradInput = nobackward('nn.DenseMatch')
+
+-- ---------------------------------------------------------------- extractoutput
+extractoutput = {}
+function extractoutput.extractOutput(input, scores, threshold, ret)
+   local inp = input:contiguous()
+   dm.check(C.dm_extract_output(ctx, torch.data(inp), inp:size(1), inp:size(2), inp:size(3), threshold,
+                                torch.data(ret), torch.data(scores), nil))
+end
+function extractoutput.extractOutputMarginalized(input, threshold, threshold_acc, ret, retgd)
+   local inp = input:contiguous()
+   dm.check(C.dm_extract_output_marginalized(ctx, torch.data(inp), inp:size(1), inp:size(2), inp:size(3),
+                                             threshold, threshold_acc, torch.data(ret), torch.data(retgd)))
+end
+package.loaded['extractoutput'] = extractoutput
+
+-- ---------------------------------------------------------------- x2yxMulti2
+-- same signature and return order as opticalflow_model_multiscale.lua:72-81; no gcc at run time
+function x2yxMulti2(geometry, x, bug_compat)
+   local retx = torch.LongTensor():resizeAs(x):zero()
+   local rety = torch.LongTensor():resizeAs(x):zero()
+   local rat = ffi.new('int[?]', #geometry.ratios, geometry.ratios)
+   dm.check(C.dm_x2yx_multi(ctx, torch.data(x), x:size(1), x:size(2), geometry.maxh, geometry.maxw, rat,
+                            #geometry.ratios, bug_compat and 1 or 0, torch.data(rety), torch.data(retx)))
+   return rety, retx
+end

@@ -1,0 +1,101 @@
+"""Generates tests/golden/*.npz.  Run in the authoring container (where /root/reference is
+mounted and oracle/_ref is built from the reference's own sources):
+
+    python tests/golden/make_golden.py
+
+Two kinds of vectors:
+  * ref_*.npz    -- inputs + outputs of the REFERENCE's own native code (oracle/_ref:
+                    version2/extract_output.cpp, x2yxMulti2.c compiled as-is).  These pin the
+                    oracle (tests/test_golden.py, CPU) and the CUDA kernels (GPU).
+  * oracle_*.npz -- inputs + outputs of the oracle restatement for the parts whose arithmetic
+                    lives in un-vendored Torch7 code (matching, softmax, cascade, polar remap):
+                    regression vectors, they pin the CUDA path to the oracle across rounds and
+                    the oracle to itself (parity with the real reference is unpinned there).
+"""
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import oracle_lib as O  # noqa: E402
+from synth import make_pair  # noqa: E402
+
+
+def main():
+    assert O.ref() is not None, "build oracle/_ref first (make -C oracle)"
+    rng = np.random.default_rng(20261018)
+
+    # ---- reference native code: extractOutput / extractOutputMarginalized
+    out = {}
+    for i, (n, thr) in enumerate([(9, 0.11), (33, 0.11), (289, 0.11), (64, 0.21), (25, 0.0)]):
+        inp = (rng.random((5, 8, n), dtype=np.float32) * (0.45 if n < 64 else 0.2)).astype(np.float32)
+        inp[0, 0] = 0
+        inp[1, 1] = inp[1, 1, 0]
+        r0 = rng.integers(-3, 3, (5, 8)).astype(np.int64)
+        s0 = rng.random((5, 8)).astype(np.float32)
+        ret, sc, _ = O.extract_output(inp, thr, r0, s0, "ref")
+        mret, mgd = O.extract_output_marginalized(inp, thr, 0.6, r0, "ref")
+        out.update({"in%d" % i: inp, "thr%d" % i: np.float64(thr), "r0_%d" % i: r0, "s0_%d" % i: s0,
+                    "ret%d" % i: ret, "sc%d" % i: sc, "mret%d" % i: mret, "mgd%d" % i: mgd})
+    np.savez_compressed(os.path.join(HERE, "ref_extract_output.npz"), **out)
+
+    # ---- reference native code: x2yxMulti2.c
+    out = {}
+    for i, (mh, mw, rat) in enumerate([(8, 8, [1, 2]), (8, 8, [1, 2, 4]), (16, 16, [1, 2, 4])]):
+        L = O.multiscale_length(mh, mw, rat)
+        x = np.arange(-2, L + 38 + (L % 2), dtype=np.int64).reshape(2, -1)
+        ry, rx = O.x2yx_multi2_bugcompat(x, mh, mw, rat, "ref", fill=0)
+        out.update({"x%d" % i: x, "geom%d" % i: np.array([mh, mw] + rat), "rety%d" % i: ry, "retx%d" % i: rx})
+    np.savez_compressed(os.path.join(HERE, "ref_x2yxmulti2.npz"), **out)
+
+    # ---- oracle: single-scale fused path
+    maxh, maxw = 5, 7
+    in1, in2, flow = make_pair(3, 28, 46, maxh, maxw, seed=99, noise=0.4)
+    K = maxh * maxw
+    vol = O.spatial_matching(in1, in2, maxh, maxw)
+    prob = O.neg_softmax(vol)
+    middle = (math.ceil(maxh / 2) - 1) * maxw + math.ceil(maxw / 2)
+    idx, pmax = O.argmax_tie(prob, K, middle)
+    shp = in1.shape[1:]
+    ret, sc, _ = O.extract_output(prob.reshape(shp + (K,)), 0.11)
+    ym, xm = O.soft_mean(prob, maxh, maxw)
+    np.savez_compressed(os.path.join(HERE, "oracle_single_scale.npz"), in1=in1, in2=in2, flow=flow,
+                        window=np.array([maxh, maxw]), volume=vol, prob=prob.astype(np.float32),
+                        index=idx.reshape(shp), pmax=pmax.reshape(shp), index_thr=ret, score_thr=sc,
+                        soft_y=ym.reshape(shp), soft_x=xm.reshape(shp),
+                        gap=O.top2_relgap(prob, K).reshape(shp),
+                        canvas=O.flow_canvas(idx, shp[0], shp[1], maxh, maxw, 28, 46))
+
+    # ---- oracle: cascade + ring join + radial
+    ratios = [1, 2, 4]
+    casc_in = rng.random((3, 11, 8, 8)).astype(np.float32)
+    casc = O.cascade_add(casc_in, ratios)
+    f2 = rng.standard_normal((4, 30, 20)).astype(np.float32)
+    f1 = (np.roll(f2, -3, axis=1)[:, :22] + 0.1 * rng.standard_normal((4, 22, 20))).astype(np.float32)
+    rvol = O.radial_matching(f1, f2, 9)
+    ridx, rmin = O.argmin_tie(rvol, 9, 0)
+    np.savez_compressed(os.path.join(HERE, "oracle_multiscale_radial.npz"), casc_in=casc_in, casc=casc,
+                        ring=O.ring_join(casc, ratios), ratios=np.array(ratios), rf1=f1, rf2=f2,
+                        rvol=rvol, rflow=(ridx - 1).reshape(22, 20).astype(np.float32))
+
+    # ---- oracle: polar remap
+    hImg, wImg, hIn, wIn = 45, 80, 50, 48
+    e2 = (641.4552 * wImg / 1280.0, 344.950836 * wImg / 1280.0)
+    img = rng.random((2, hImg, wImg)).astype(np.float32)
+    rmax = O.get_rmax(hImg, wImg, *e2)
+    m = O.c2p_mask(wIn, hIn, e2[0], e2[1], 2, 3, rmax, 1.0)
+    pol = O.warp_bilinear(img, m)
+    m2 = O.p2c_mask(wIn, hIn, wImg, hImg, e2[0], e2[1], rmax, 1.0)
+    back = O.warp_bilinear(pol[:, :, 2:2 + wIn], m2)
+    np.savez_compressed(os.path.join(HERE, "oracle_polar.npz"), img=img, e2=np.array(e2), rmax=np.float64(rmax),
+                        geom=np.array([hImg, wImg, hIn, wIn, 2, 3]), c2p=m, polar=pol, p2c=m2, back=back)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,111 @@
+"""Committed golden vectors (tests/golden/, made by make_golden.py).  ref_*.npz come from the
+reference's own native sources; oracle_*.npz are regression vectors of the oracle.  CPU tests
+check the oracle against them, GPU tests check the CUDA path (through the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+def test_oracle_extract_output_matches_reference_vectors(oracle):
+    z = load("ref_extract_output.npz")
+    for i in range(5):
+        ret, sc, _ = oracle.extract_output(z["in%d" % i], float(z["thr%d" % i]), z["r0_%d" % i], z["s0_%d" % i])
+        np.testing.assert_array_equal(ret, z["ret%d" % i])
+        np.testing.assert_array_equal(sc, z["sc%d" % i])
+        mret, mgd = oracle.extract_output_marginalized(z["in%d" % i], float(z["thr%d" % i]), 0.6, z["r0_%d" % i])
+        np.testing.assert_array_equal(mret, z["mret%d" % i])
+        np.testing.assert_array_equal(mgd, z["mgd%d" % i])
+
+
+def test_oracle_x2yxmulti2_matches_reference_vectors(oracle):
+    z = load("ref_x2yxmulti2.npz")
+    for i in range(3):
+        g = z["geom%d" % i]
+        ry, rx = oracle.x2yx_multi2_bugcompat(z["x%d" % i], int(g[0]), int(g[1]), [int(v) for v in g[2:]], fill=0)
+        np.testing.assert_array_equal(ry, z["rety%d" % i])
+        np.testing.assert_array_equal(rx, z["retx%d" % i])
+
+
+def test_oracle_regression_vectors(oracle):
+    z = load("oracle_single_scale.npz")
+    maxh, maxw = [int(v) for v in z["window"]]
+    vol = oracle.spatial_matching(z["in1"], z["in2"], maxh, maxw)
+    np.testing.assert_array_equal(vol, z["volume"])
+    np.testing.assert_array_equal(oracle.neg_softmax(vol), z["prob"])
+    z = load("oracle_multiscale_radial.npz")
+    np.testing.assert_array_equal(oracle.cascade_add(z["casc_in"], list(z["ratios"])), z["casc"])
+    np.testing.assert_array_equal(oracle.ring_join(z["casc"], list(z["ratios"])), z["ring"])
+    np.testing.assert_array_equal(oracle.radial_matching(z["rf1"], z["rf2"], 9), z["rvol"])
+    z = load("oracle_polar.npz")
+    hImg, wImg, hIn, wIn, lp, rp = [int(v) for v in z["geom"]]
+    m = oracle.c2p_mask(wIn, hIn, z["e2"][0], z["e2"][1], lp, rp, float(z["rmax"]), 1.0)
+    np.testing.assert_array_equal(m, z["c2p"])
+    np.testing.assert_array_equal(oracle.warp_bilinear(z["img"], m), z["polar"])
+
+
+@pytest.mark.gpu
+def test_cuda_extract_output_matches_reference_vectors(dm):
+    z = load("ref_extract_output.npz")
+    for i in range(5):
+        ret, sc = z["r0_%d" % i].copy(), z["s0_%d" % i].copy()
+        dm.extractoutput.extractOutput(z["in%d" % i], sc, float(z["thr%d" % i]), ret)
+        np.testing.assert_array_equal(ret, z["ret%d" % i])
+        np.testing.assert_array_equal(sc, z["sc%d" % i])
+        ret, gd = z["r0_%d" % i].copy(), np.full(ret.shape, 5, np.int64)
+        dm.extractoutput.extractOutputMarginalized(z["in%d" % i], float(z["thr%d" % i]), 0.6, ret, gd)
+        np.testing.assert_array_equal(ret, z["mret%d" % i])
+        np.testing.assert_array_equal(gd, z["mgd%d" % i])
+
+
+@pytest.mark.gpu
+def test_cuda_x2yxmulti2_bugcompat_matches_reference_vectors(dm):
+    z = load("ref_x2yxmulti2.npz")
+    for i in range(3):
+        g = z["geom%d" % i]
+        geo = dm.Geometry(maxh=int(g[0]), maxw=int(g[1]), ratios=[int(v) for v in g[2:]], multiscale=True)
+        ry, rx = dm.x2yxMulti2(geo, z["x%d" % i], bug_compat=True)
+        np.testing.assert_array_equal(ry, z["rety%d" % i])
+        np.testing.assert_array_equal(rx, z["retx%d" % i])
+
+
+@pytest.mark.gpu
+def test_cuda_fused_path_matches_oracle_vectors(dm):
+    z = load("oracle_single_scale.npz")
+    maxh, maxw = [int(v) for v in z["window"]]
+    got = dm.match_extract(z["in1"], z["in2"], maxh, maxw, exact=True, canvas=(28, 46),
+                           want=("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx"))
+    tie = z["gap"] < 1e-5
+    assert ((got["index"] != z["index"]) & ~tie).sum() == 0
+    np.testing.assert_array_equal(got["min_ssd"], z["volume"].reshape(z["index"].shape + (-1,)).min(-1))
+    np.testing.assert_allclose(got["pmax"], z["pmax"], rtol=1e-4)
+    np.testing.assert_allclose(got["soft_yx"][0], z["soft_y"], rtol=1e-4)
+    np.testing.assert_allclose(got["soft_yx"][1], z["soft_x"], rtol=1e-4)
+    prob = z["prob"].reshape(z["index"].shape + (-1,))
+    ok = ~((np.abs(prob - 0.11) < 0.11 * 4e-5).any(-1) | tie)
+    np.testing.assert_array_equal(got["index_thr"][ok], z["index_thr"][ok])
+    np.testing.assert_allclose(got["score_thr"][ok], z["score_thr"][ok], rtol=1e-4, atol=1e-7)
+    if not tie.any():
+        np.testing.assert_array_equal(got["flow_full"], z["canvas"])
+    np.testing.assert_array_equal(dm.match_volume(z["in1"], z["in2"], maxh, maxw, exact=True), z["volume"])
+
+
+@pytest.mark.gpu
+def test_cuda_cascade_radial_polar_match_oracle_vectors(dm):
+    z = load("oracle_multiscale_radial.npz")
+    ratios = [int(v) for v in z["ratios"]]
+    got = dm.nn.CascadingAddTable(ratios).forward([z["casc_in"][i] for i in range(3)])
+    for i in range(3):
+        np.testing.assert_array_equal(got[i], z["casc"][i])
+    flow, _ = dm.nn.SpatialRadialMatching(9).argmin_flow([z["rf1"], z["rf2"]])
+    np.testing.assert_array_equal(flow, z["rflow"])
+    z = load("oracle_polar.npz")
+    np.testing.assert_array_equal(dm.cartesian2polar(z["img"], z["c2p"]), z["polar"])
+    lp, wIn = int(z["geom"][4]), int(z["geom"][3])
+    np.testing.assert_array_equal(dm.cartesian2polar(z["polar"][:, :, lp:lp + wIn], z["p2c"]), z["back"])
