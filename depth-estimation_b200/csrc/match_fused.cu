@@ -14,6 +14,9 @@
 // Numerics: SSD in fp32, channel-ascending, FMA-contracted unless DM_FLAG_EXACT_SSD;
 // the softmax runs online (flash-style running minimum) with ex2.approx, so
 // probabilities agree with the two-pass CPU path to ~1e-6 relative, not bit-wise.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "match_kernels.cuh"
 
 namespace dm {
@@ -51,8 +54,13 @@ struct ExtractParams {
 template <bool SOFT>
 struct ExtractEpi {
   const ExtractParams &P;
-  float m[kP], v2[kP], S[kP], sx[kP], sy[kP];  // v2: second smallest SSD among shortlisted entries
+  float m[kP], S[kP], sx[kP], sy[kP];
   int idx[kP];
+  // thresholded extraction: e2[p] = upper bound of the second largest exp(m - v) seen so far
+  // (relative to the running minimum, rescaled with it); vfrom[p] = first shortlist bit still
+  // in reach of the threshold
+  float e2[kP];
+  int vfrom[kP];
   unsigned *mask;  // [nwords][kP][kCThreads] words, this thread's column
   float *vmid;     // [kP][kCThreads]
 
@@ -64,9 +72,11 @@ struct ExtractEpi {
   __device__ __forceinline__ void tile_begin(int, int, int) {
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
-      m[p] = v2[p] = __int_as_float(0x7f800000);
+      m[p] = __int_as_float(0x7f800000);
       S[p] = sx[p] = sy[p] = 0.0f;
       idx[p] = 1;
+      e2[p] = 0.0f;
+      vfrom[p] = 0;
       vmid[p * kCThreads] = 0.0f;
     }
     for (int w = 0; w < P.nwords * kP; ++w) mask[w * kCThreads] = 0u;
@@ -74,22 +84,16 @@ struct ExtractEpi {
 
   // a new running minimum v at 1-based index k for pixel p (strict <: the first occurrence
   // wins, like TH max): rescale what was accumulated relative to the old one
-  __device__ __forceinline__ void new_min(int p, float v, int k) {
+  __device__ __forceinline__ void new_min(int p, float v, int k, int bit) {
     const float sc = ex2_approx((v - m[p]) * kLog2e);  // old m = +inf -> 0
     S[p] *= sc;
     if (SOFT) {
       sx[p] *= sc;
       sy[p] *= sc;
     }
-    if (P.nwords) {
-      if (sc < P.p_clear) {
-        // the old minimum (and everything before it) is now below the threshold for good
-        for (int w = 0; w < P.nwords; ++w) mask[(w * kP + p) * kCThreads] = 0u;
-        v2[p] = __int_as_float(0x7f800000);
-      } else {
-        v2[p] = fminf(v2[p], m[p]);  // the old minimum is now a runner-up
-      }
-    }
+    e2[p] = fmaxf(e2[p], 1.0f) * sc;  // the old minimum (e = 1) becomes a runner-up
+    // old minimum (and everything before it) below the threshold for good: earlier bits are dead
+    if (sc < P.p_clear) vfrom[p] = bit;
     m[p] = v;
     idx[p] = k;
   }
@@ -112,17 +116,17 @@ struct ExtractEpi {
           if (r == P.mid_r) vmid[p * kCThreads] = acc[p][r];
     }
     float bm[kP];
-    bool any = false, nm[kP];
+    bool any = false;
+    const int bit = dy * P.g.bs.per_row() + blk;
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
-      nm[p] = false;
       bm[p] = acc[p][0];
 #pragma unroll
       for (int r = 1; r < kR; ++r) bm[p] = fminf(bm[p], acc[p][r]);
       any |= bm[p] < m[p];
     }
+    const int kbase = (dy * P.g.maxw + blk * kR) + 1;  // 1-based index of r = 0
     if (any) {  // some pixel of this thread has a new running minimum in this block
-      const int kbase = (dy * P.g.maxw + blk * kR) + 1;  // 1-based index of r = 0
 #pragma unroll
       for (int p = 0; p < kP; ++p)
         if (bm[p] < m[p]) {
@@ -130,13 +134,12 @@ struct ExtractEpi {
 #pragma unroll
           for (int r = kR - 1; r >= 0; --r)
             if (acc[p][r] == bm[p]) rb = r;
-          new_min(p, bm[p], kbase + rb);
-          nm[p] = true;
+          new_min(p, bm[p], kbase + rb, bit);
         }
     }
     const float rowf = (float)(dy + 1), colf = (float)(blk * kR);
     bool cand = false;
-    float eb[kP];
+    float eb[kP], ebm[kP];
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
       const float mL = m[p] * kLog2e;
@@ -155,39 +158,25 @@ struct ExtractEpi {
       }
       // thresholded extraction: p_k(final) <= e_k / S(now), so an entry of this block can
       // end above the threshold only if the block's largest e exceeds thr * S
-      if (P.nwords) cand |= ex2_approx(fmaf(bm[p], -kLog2e, mL)) > P.thr_lo * S[p];
+      ebm[p] = 0.0f;
+      if (P.nwords) {
+        ebm[p] = ex2_approx(fmaf(bm[p], -kLog2e, mL));
+        cand |= ebm[p] > P.thr_lo * S[p];
+      }
     }
     if (cand) {
-      const int bit = dy * P.g.bs.per_row() + blk;
 #pragma unroll
-      for (int p = 0; p < kP; ++p)
-        if (ex2_approx((m[p] - bm[p]) * kLog2e) > P.thr_lo * S[p]) {
+      for (int p = 0; p < kP; ++p) {
+        const float lim = P.thr_lo * S[p];
+        if (ebm[p] > lim) {
           mask[((bit >> 5) * kP + p) * kCThreads] |= 1u << (bit & 31);
-          // every entry that can still end above the threshold passes through here, so the
-          // second smallest SSD seen here bounds the second largest probability (tile_end)
-          float lo = m[p], hi = v2[p];
-#pragma unroll
-          for (int r = 0; r < kR; ++r) {
-            const float v = acc[p][r];
-            hi = fminf(hi, fmaxf(lo, v));
-            lo = fminf(lo, v);
-          }
-          // lo started at the running minimum so that a tie with it is recorded; when the
-          // minimum was set by this very block it must be counted once, not twice
-          v2[p] = nm[p] ? second_smallest(acc[p], v2[p]) : hi;
+          // runner-up bound: in the block that holds the minimum (first occurrence) the second
+          // largest e is at most eb - ebm; in any other block it is the block's largest e
+          const bool own = idx[p] >= kbase && idx[p] < kbase + kR;
+          e2[p] = fmaxf(e2[p], own ? eb[p] - ebm[p] : ebm[p]);
         }
+      }
     }
-  }
-
-  // second smallest of {acc[0..8)} and v2_old, where the smallest of acc is the running minimum
-  __device__ __forceinline__ static float second_smallest(const float (&v)[kR], float v2_old) {
-    float lo = __int_as_float(0x7f800000), hi = v2_old;
-#pragma unroll
-    for (int r = 0; r < kR; ++r) {
-      hi = fminf(hi, fmaxf(lo, v[r]));
-      lo = fminf(lo, v[r]);
-    }
-    return hi;
   }
 
   __device__ __forceinline__ void column(float (&acc)[kP], int dy, int blk) {
@@ -200,8 +189,7 @@ struct ExtractEpi {
     const float rowf = (float)(dy + 1), colf = (float)(blk * kR + 1);
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
-      const bool isnew = acc[p] < m[p];
-      if (isnew) new_min(p, acc[p], k);
+      if (acc[p] < m[p]) new_min(p, acc[p], k, bit);
       const float e = ex2_approx((m[p] - acc[p]) * kLog2e);
       S[p] += e;
       if (SOFT) {
@@ -210,7 +198,7 @@ struct ExtractEpi {
       }
       if (P.nwords && e > P.thr_lo * S[p]) {
         mask[((bit >> 5) * kP + p) * kCThreads] |= 1u << (bit & 31);
-        if (!isnew) v2[p] = fminf(v2[p], acc[p]);
+        if (idx[p] != k) e2[p] = fmaxf(e2[p], e);
       }
     }
   }
@@ -248,15 +236,13 @@ struct ExtractEpi {
       }
       if (P.todo) {
         // extractOutput(prob, thr) (extract_output.cpp:63-155).  pmax < thr: nothing qualifies,
-        // the pixel stays untouched.  pmax > thr and the second largest probability
-        // exp(m - v2)/S < thr: the list is {pmax}, ret = its position, score = M * pmax (prefix
-        // sums of {pmax,0,..}).  Anything within 1e-4 of those borders, and every pixel with two
-        // or more entries above the threshold, goes to the exact per-pixel pass, which re-scores
-        // only the (dy, dx-block)s on the pixel's shortlist.
+        // the pixel stays untouched.  pmax > thr and the runner-up bound e2/S < thr: the list is
+        // {pmax}, ret = its position, score = M * pmax (prefix sums of {pmax,0,..}).  Anything within 1e-4 of the threshold, and every pixel that may have
+        // two or more entries above it, goes to the exact per-pixel pass, which re-scores only
+        // the (dy, dx-block)s on the pixel's shortlist.
         long long ret = 0;
         float score = 0.0f;
-        const float p2 = expf(m[p] - v2[p]) * inv;
-        if (inv > P.p_gt && p2 < P.p_none) {
+        if (inv > P.p_gt && e2[p] * inv < P.p_none) {
           ret = idx[p];
           score = (float)((double)P.M * (double)inv);
         } else if (inv < P.p_none) {
@@ -264,8 +250,13 @@ struct ExtractEpi {
         } else {
           const unsigned slot = atomicAdd(P.ntodo, 1u);
           P.todo[slot] = (int)o;
-          for (int w = 0; w < P.nwords; ++w)
-            P.todo_mask[(size_t)slot * P.nwords + w] = mask[(w * kP + p) * kCThreads];
+          for (int w = 0; w < P.nwords; ++w) {
+            unsigned bits = mask[(w * kP + p) * kCThreads];
+            const int lo = vfrom[p] - 32 * w;  // bits below vfrom are dead
+            if (lo >= 32) bits = 0u;
+            else if (lo > 0) bits &= ~0u << lo;
+            P.todo_mask[(size_t)slot * P.nwords + w] = bits;
+          }
           P.vmin[o] = m[p];
           P.vinv[o] = inv;
         }
@@ -747,6 +738,12 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
     threshold_exact_kernel<<<ctx->num_sms * 12, 128, 0, ctx->stream>>>(T);
     DM_CUDA(cudaGetLastError());
     count_launch(ctx);
+    if (getenv("DM_DEBUG_TODO")) {  // diagnostics: how many pixels needed the exact pass
+      unsigned n = 0;
+      cudaMemcpyAsync(&n, P.ntodo, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      fprintf(stderr, "[depthmatch] exact pass: %u of %zu pixels\n", n, npx);
+    }
   }
   return call.finish();
 }
