@@ -259,8 +259,13 @@ def main():
     in1_p = crop(f1_p).numpy()
     f2_pn = f2_p.numpy()
 
+    # results land in pinned host buffers too (what a host that consumes them every frame keeps)
+    shapes = {"index": ((B, H1, W1), torch.int64), "pmax": ((B, H1, W1), torch.float32),
+              "score_thr": ((B, H1, W1), torch.float32), "flow_full": ((B, 2, H, W), torch.float32)}
+    out_p = {k: torch.empty(shp, dtype=dt).pin_memory().numpy() for k, (shp, dt) in shapes.items()}
+
     def e2e_step():
-        return dm.match_extract(in1_p, f2_pn, MAXH, MAXW, canvas=(H, W), want=want, ctx=ctx)
+        return dm.match_extract(in1_p, f2_pn, MAXH, MAXW, canvas=(H, W), want=want, ctx=ctx, out=out_p)
 
     e2e_step()
     barrier()

@@ -44,6 +44,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 struct Arena {
   char *base = nullptr;
   size_t cap = 0, used = 0;
+  size_t demand = 0;  // bytes the current call asked for in total (arena + overflow blocks)
 };
 
 }  // namespace dm
@@ -66,6 +67,10 @@ struct dm_ctx {
   };
   std::vector<Pending> pending;
   bool call_has_host = false;
+  // two private sub-contexts (own stream + arena) used to pipeline host-buffer batches:
+  // H2D of chunk i+1 overlaps the kernels of chunk i and the D2H of chunk i-1
+  dm_ctx *pipe[2] = {nullptr, nullptr};
+  bool is_child = false;
 };
 
 namespace dm {
@@ -79,7 +84,8 @@ PtrKind classify(const void *p);
 // was involved.
 struct Call {
   dm_ctx *ctx;
-  explicit Call(dm_ctx *c);
+  bool defer = false;  // leave the final synchronise to the caller (pipelined chunks)
+  explicit Call(dm_ctx *c, bool defer_sync = false);
   int alloc(void **dptr, size_t bytes);  // device scratch, 256-byte aligned
   int in(const void *user, size_t bytes, const void **dptr);
   // like in() but a pitched 2D copy: rows of row_bytes, user pitch -> dense device rows

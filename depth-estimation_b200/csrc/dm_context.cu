@@ -52,7 +52,11 @@ int ensure_arena(dm_ctx *ctx, size_t bytes) {
   return DM_OK;
 }
 
-Call::Call(dm_ctx *c) : ctx(c) {
+Call::Call(dm_ctx *c, bool defer_sync) : ctx(c), defer(defer_sync) {
+  // size the arena for what the previous call needed, so that steady-state calls never fall
+  // back to per-call cudaMalloc blocks
+  if (ctx->arena.demand > ctx->arena.cap) ensure_arena(ctx, ctx->arena.demand);
+  ctx->arena.demand = 0;
   ctx->arena.used = 0;
   ctx->pending.clear();
   ctx->call_has_host = false;
@@ -70,6 +74,7 @@ static thread_local std::vector<void *> g_extra;
 
 int Call::alloc(void **dptr, size_t bytes) {
   const size_t aligned = (bytes + 255) & ~size_t(255);
+  ctx->arena.demand += aligned;
   if (ctx->arena.used + aligned > ctx->arena.cap) {
     if (ctx->arena.used == 0) {
       DM_CHECK(ensure_arena(ctx, aligned));
@@ -125,7 +130,7 @@ int Call::finish() {
     if (e != cudaSuccess && rc == DM_OK) rc = cuda_fail(e, "copy-back", __FILE__, __LINE__);
   }
   ctx->pending.clear();
-  if (ctx->call_has_host || !g_extra.empty()) {
+  if ((ctx->call_has_host && !defer) || !g_extra.empty()) {
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess && rc == DM_OK) rc = cuda_fail(e, "stream synchronize", __FILE__, __LINE__);
   }
@@ -220,6 +225,8 @@ int dm_create(int device, dm_ctx **out) {
 int dm_destroy(dm_ctx *ctx) {
   if (!ctx) return DM_OK;
   cudaSetDevice(ctx->device);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->pipe[i]) dm_destroy(ctx->pipe[i]);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

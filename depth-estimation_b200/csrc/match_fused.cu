@@ -626,11 +626,9 @@ static int grid_for(dm_ctx *ctx, const void *kernel, size_t smem, int ntiles) {
 
 using namespace dm;
 
-extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, unsigned flags,
-                                double prob_threshold, int h_img, int w_img,
-                                const dm_extract_out *out) {
-  DM_REQUIRE(ctx && in && out, "dm_match_extract: NULL argument");
-  DM_CUDA(cudaSetDevice(ctx->device));
+static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, unsigned flags,
+                              double prob_threshold, int h_img, int w_img, const dm_extract_out *out,
+                              bool defer) {
   const bool want_thr = out->index_thr || out->score_thr || out->n_untouched;
   DM_REQUIRE(!want_thr || (prob_threshold > 0.1 && prob_threshold < 1.0),
              "dm_match_extract: fused thresholded extraction needs 0.1 < prob_threshold < 1 "
@@ -639,7 +637,7 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
   if (out->flow_full)
     DM_REQUIRE(h_img >= in->h1 && w_img >= in->w1, "canvas %dx%d smaller than output %dx%d", h_img,
                w_img, in->h1, in->w1);
-  Call call(ctx);
+  Call call(ctx, defer);
   if (in->channels > kMaxC) {
     int rc = generic_match_extract(call, in, maxh, maxw, flags, prob_threshold, h_img, w_img, out);
     int rf = call.finish();
@@ -746,6 +744,62 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
     }
   }
   return call.finish();
+}
+
+// Host-buffer batches are cut in chunks that alternate between two private sub-contexts, so
+// the H2D copy of one chunk overlaps the kernels of the previous one and the D2H of the one
+// before (full-duplex PCIe + compute); device-buffer calls go straight through.
+extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, unsigned flags,
+                                double prob_threshold, int h_img, int w_img,
+                                const dm_extract_out *out) {
+  DM_REQUIRE(ctx && in && out, "dm_match_extract: NULL argument");
+  DM_CUDA(cudaSetDevice(ctx->device));
+  const bool host_in = in->in1 && in->in2 && classify(in->in1) == PtrKind::Host &&
+                       classify(in->in2) == PtrKind::Host;
+  const int N = in->n_pairs;
+  if (!host_in || N < 4 || ctx->is_child || getenv("DM_NO_PIPELINE"))
+    return match_extract_impl(ctx, in, maxh, maxw, flags, prob_threshold, h_img, w_img, out, false);
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->pipe[i]) {
+      DM_CHECK(dm_create(ctx->device, &ctx->pipe[i]));
+      ctx->pipe[i]->is_child = true;
+    }
+  const long long s1y = in->in1_stride_y ? in->in1_stride_y : in->w1;
+  const long long s1c = in->in1_stride_c ? in->in1_stride_c : (long long)in->h1 * s1y;
+  const long long s1n = in->in1_stride_n ? in->in1_stride_n : (long long)in->channels * s1c;
+  const long long s2y = in->in2_stride_y ? in->in2_stride_y : in->w2;
+  const long long s2c = in->in2_stride_c ? in->in2_stride_c : (long long)in->h2 * s2y;
+  const long long s2n = in->in2_stride_n ? in->in2_stride_n : (long long)in->channels * s2c;
+  const size_t npx1 = (size_t)in->h1 * in->w1, canvas = (size_t)2 * h_img * w_img;
+  int chunk = N >= 16 ? 4 : (N >= 8 ? 2 : 1);  // 4 north pairs = 3 full waves of tiles on 148 SMs
+  if (const char *e = getenv("DM_PIPE_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+  int rc = DM_OK;
+  for (int n0 = 0, c = 0; n0 < N && rc == DM_OK; n0 += chunk, ++c) {
+    dm_pair sub = *in;
+    sub.n_pairs = N - n0 < chunk ? N - n0 : chunk;
+    sub.in1 = in->in1 + n0 * s1n;
+    sub.in2 = in->in2 + n0 * s2n;
+    sub.in1_stride_n = s1n; sub.in1_stride_c = s1c; sub.in1_stride_y = s1y;
+    sub.in2_stride_n = s2n; sub.in2_stride_c = s2c; sub.in2_stride_y = s2y;
+    dm_extract_out so = *out;
+    if (so.index) so.index += n0 * npx1;
+    if (so.min_ssd) so.min_ssd += n0 * npx1;
+    if (so.pmax) so.pmax += n0 * npx1;
+    if (so.flow_full) so.flow_full += n0 * canvas;
+    if (so.index_thr) so.index_thr += n0 * npx1;
+    if (so.score_thr) so.score_thr += n0 * npx1;
+    if (so.soft_yx) so.soft_yx += n0 * 2 * npx1;
+    if (so.n_untouched) so.n_untouched += n0;
+    rc = match_extract_impl(ctx->pipe[c & 1], &sub, maxh, maxw, flags, prob_threshold, h_img, w_img, &so,
+                            true);
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaStreamSynchronize(ctx->pipe[i]->stream);
+    if (e != cudaSuccess && rc == DM_OK) rc = cuda_fail(e, "pipeline synchronize", __FILE__, __LINE__);
+    ctx->launches += ctx->pipe[i]->launches;
+    ctx->pipe[i]->launches = 0;
+  }
+  return rc;
 }
 
 // ---------------------------------------------------------------- volume API

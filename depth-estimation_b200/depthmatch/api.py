@@ -198,9 +198,11 @@ def match_volume(in1, in2, maxh, maxw, softmax=False, exact=False, ctx=None):
 
 def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_threshold=0.11,
                   canvas=None, want=("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx"),
-                  ctx=None):
+                  ctx=None, out=None):
     """Fused prepareInput-less forward + processOutput.  Returns a dict of arrays, each
-    [N,]H1,W1 (soft_yx: [N,]2,H1,W1; flow_full: [N,]2,hImg,wImg when canvas=(hImg,wImg))."""
+    [N,]H1,W1 (soft_yx: [N,]2,H1,W1; flow_full: [N,]2,hImg,wImg when canvas=(hImg,wImg)).
+    `out` may hold preallocated result buffers by name (e.g. pinned host memory), with the
+    batched shapes [N,...]; they are written in place and returned."""
     args = _Args(ctx)
     single = (in1.dim() if _is_torch(in1) else np.ndim(in1)) == 3
     p, a, b = _pair_struct(args, in1, in2)
@@ -222,7 +224,13 @@ def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_thres
             shape, dt = (N, 2, int(canvas[0]), int(canvas[1])), np.float32
         else:
             shape, dt = shapes[name]
-        ptr, arr = args.out(shape, dt, like=a)
+        if out is not None and name in out:
+            arr = out[name]
+            _check_inplace(arr, dt, shape)
+            args.keep.append(arr)
+            ptr = _ptr(arr)
+        else:
+            ptr, arr = args.out(shape, dt, like=a)
         setattr(o, name, ptr)
         res[name] = arr
     flags = (DM_FLAG_TIE_MIDDLE if tie_middle else 0) | (DM_FLAG_EXACT_SSD if exact else 0)

@@ -397,3 +397,24 @@ def test_north_config_full_size_properties(dm):
     ex = dm.match_extract(in1, in2, maxh, maxw, exact=True, want=("index", "min_ssd"))
     np.testing.assert_array_equal(ex["index"], got["index"])
     np.testing.assert_allclose(ex["min_ssd"], got["min_ssd"], rtol=RTOL)
+
+
+def test_pipelined_host_batch_matches_single_calls(dm):
+    """Host batches of >= 4 pairs are cut in chunks over two streams; same results as pair by pair."""
+    maxh, maxw, C, N = 9, 17, 10, 7
+    f1 = np.empty((N, C, 40, 72), np.float32)
+    f2 = np.empty((N, C, 40, 72), np.float32)
+    oy, ox = math.ceil(maxh / 2) - 1, math.ceil(maxw / 2) - 1
+    H1, W1 = 40 - maxh + 1, 72 - maxw + 1
+    for n in range(N):
+        in1, in2, _ = make_pair(C, 40, 72, maxh, maxw, seed=50 + n, noise=0.5)
+        f1[n] = 0
+        f1[n, :, oy:oy + H1, ox:ox + W1] = in1
+        f2[n] = in2
+    view = f1[:, :, oy:oy + H1, ox:ox + W1]
+    want = ("index", "pmax", "index_thr", "score_thr", "soft_yx", "min_ssd", "n_untouched")
+    batch = dm.match_extract(view, f2, maxh, maxw, canvas=(40, 72), want=want)
+    for n in range(N):
+        one = dm.match_extract(view[n], f2[n], maxh, maxw, canvas=(40, 72), want=want)
+        for k in one:
+            np.testing.assert_array_equal(batch[k][n], one[k], err_msg=k)
