@@ -53,47 +53,56 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md), polled in-process
+    through NVML (pynvml): spawning nvidia-smi in a loop takes driver locks for tens of
+    milliseconds and perturbs a sub-second timed region."""
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.ok, self._stop = [], False, False
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.ok = False
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, [n for n, bit in names.items() if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def wait_first(self, timeout=5.0):
-        """nvidia-smi's start-up takes driver locks: let it settle before anything is timed."""
         t0 = time.time()
-        while self.proc and not self.rows and time.time() - t0 < timeout:
-            time.sleep(0.05)
+        while self.ok and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
 
     def mark(self):
         return len(self.rows)
 
     def summary(self, start, stop):
         rows = self.rows[start:stop] or self.rows[-3:]
-        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        sm = [r[0] for r in rows]
+        reasons = sorted({n for r in rows for n in r[1]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": getattr(self, "max", None),
                 "reasons": reasons, "samples": len(rows)}
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        self._stop = True
 
 
 def make_batch(B, seed0):
@@ -219,6 +228,19 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.wait_first()
+    # untimed settle phase: a box that just ran another process (memory scrubbing, clock ramp)
+    # needs a moment before step times are steady; then the W contractual warm-up steps
+    prev = None
+    for _ in range(30):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        e1.synchronize()
+        cur = e0.elapsed_time(e1)
+        if prev is not None and abs(cur - prev) < 0.03 * prev:
+            break
+        prev = cur
     for _ in range(args.warmup):
         step()
     barrier()
@@ -226,16 +248,19 @@ def main():
     mark0 = sampler.mark() if sampler else 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
+    step_evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         out = step()
-        kernel_ms.append(None)
+        step_evs[i].record()
     ev1.record()
     barrier()
     mark1 = sampler.mark() if sampler else 0
     launches = ctx.launch_count() - l0
     ms_total = ev0.elapsed_time(ev1)
-    last_kernel_ms = ctx.last_kernel_ms()
+    per_step = [(ev0 if i == 0 else step_evs[i - 1]).elapsed_time(step_evs[i]) for i in range(args.steps)]
+    if os.environ.get("DM_BENCH_DEBUG"):
+        print("per-step ms: " + " ".join("%.2f" % v for v in per_step), file=sys.stderr)
     t = torch.tensor([ms_total], device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

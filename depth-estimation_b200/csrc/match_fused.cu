@@ -31,7 +31,7 @@ struct ExtractParams {
   float p_gt;         // a probability above this is above the threshold for sure (thr + 1e-4)
   float thr_lo;       // shortlist trigger: e_k > thr_lo * S (thr_lo slightly under thr)
   float p_clear;      // rescale factor under which everything seen before a new minimum is out
-  int mid_dy, mid_blk, mid_r, middle;  // zero-flow entry (dy, dx-block, column in block; 1-based index)
+  int mid_dy, mid_blk[2], mid_r[2], middle;  // zero-flow entry: dy, then (block, column) for even / odd pixels; 1-based index
   int cy, cx;                          // ceil(maxh/2), ceil(maxw/2)
   int h_img, w_img, hoff, woff;
   long long *index;
@@ -98,22 +98,32 @@ struct ExtractEpi {
     idx[p] = k;
   }
 
-  __device__ __forceinline__ void block(float (&acc)[kP][kR], int dy, int blk, int rvalid) {
+  // acc[p][r] is the SSD of pixel p at dx = 8*blk - (p & 1) + r (skewed blocks, see
+  // BlockSchedule); R = 8, or 2 for a narrow tail
+  template <int R>
+  __device__ __forceinline__ void block(float (&acc)[kP][R], int dy, int blk) {
     const float inf = __int_as_float(0x7f800000);
-    if (rvalid < kR) {
+    const int dx0 = blk * kR;  // dx of r = 0 for even pixels; odd pixels start one earlier
+    // entries outside the window (warp-uniform branches): dx = -1 of the odd pixels in the
+    // first block, dx >= maxw in the last one
+    if (blk == 0) {
 #pragma unroll
-      for (int p = 0; p < kP; ++p)
-#pragma unroll
-        for (int r = 0; r < kR; ++r)
-          if (r >= rvalid) acc[p][r] = inf;
+      for (int p = 1; p < kP; p += 2) acc[p][0] = inf;
     }
-    // zero-flow entry, for the tie rule (warp-uniform branch, once per sweep)
-    if (dy == P.mid_dy && blk == P.mid_blk) {
+    if (dx0 + R > P.g.maxw) {
 #pragma unroll
       for (int p = 0; p < kP; ++p)
 #pragma unroll
-        for (int r = 0; r < kR; ++r)
-          if (r == P.mid_r) vmid[p * kCThreads] = acc[p][r];
+        for (int r = 0; r < R; ++r)
+          if (dx0 - (p & 1) + r >= P.g.maxw) acc[p][r] = inf;
+    }
+    // zero-flow entry, for the tie rule (warp-uniform branch, once or twice per sweep)
+    if (dy == P.mid_dy && (blk == P.mid_blk[0] || blk == P.mid_blk[1])) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (blk == P.mid_blk[p & 1] && r == P.mid_r[p & 1]) vmid[p * kCThreads] = acc[p][r];
     }
     float bm[kP];
     bool any = false;
@@ -122,22 +132,22 @@ struct ExtractEpi {
     for (int p = 0; p < kP; ++p) {
       bm[p] = acc[p][0];
 #pragma unroll
-      for (int r = 1; r < kR; ++r) bm[p] = fminf(bm[p], acc[p][r]);
+      for (int r = 1; r < R; ++r) bm[p] = fminf(bm[p], acc[p][r]);
       any |= bm[p] < m[p];
     }
-    const int kbase = (dy * P.g.maxw + blk * kR) + 1;  // 1-based index of r = 0
+    const int kbase = dy * P.g.maxw + dx0 + 1;  // 1-based index of (even pixel, r = 0)
     if (any) {  // some pixel of this thread has a new running minimum in this block
 #pragma unroll
       for (int p = 0; p < kP; ++p)
         if (bm[p] < m[p]) {
           int rb = 0;
 #pragma unroll
-          for (int r = kR - 1; r >= 0; --r)
+          for (int r = R - 1; r >= 0; --r)
             if (acc[p][r] == bm[p]) rb = r;
-          new_min(p, bm[p], kbase + rb, bit);
+          new_min(p, bm[p], kbase - (p & 1) + rb, bit);
         }
     }
-    const float rowf = (float)(dy + 1), colf = (float)(blk * kR);
+    const float rowf = (float)(dy + 1);
     bool cand = false;
     float eb[kP], ebm[kP];
 #pragma unroll
@@ -146,14 +156,14 @@ struct ExtractEpi {
       float ex = 0.0f;
       eb[p] = 0.0f;
 #pragma unroll
-      for (int r = 0; r < kR; ++r) {
+      for (int r = 0; r < R; ++r) {
         const float e = ex2_approx(fmaf(acc[p][r], -kLog2e, mL));
         eb[p] += e;
         if (SOFT) ex = fmaf(e, (float)(r + 1), ex);
       }
       S[p] += eb[p];
       if (SOFT) {
-        sx[p] += fmaf(eb[p], colf, ex);
+        sx[p] += fmaf(eb[p], (float)(dx0 - (p & 1)), ex);  // column = dx + 1
         sy[p] = fmaf(eb[p], rowf, sy[p]);
       }
       // thresholded extraction: p_k(final) <= e_k / S(now), so an entry of this block can
@@ -172,33 +182,11 @@ struct ExtractEpi {
           mask[((bit >> 5) * kP + p) * kCThreads] |= 1u << (bit & 31);
           // runner-up bound: in the block that holds the minimum (first occurrence) the second
           // largest e is at most eb - ebm; in any other block it is the block's largest e
-          const bool own = idx[p] >= kbase && idx[p] < kbase + kR;
+          // (the odd pixels' dx = -1 slot of block 0 aliases the previous row's last index)
+          const int kb = kbase - (p & 1);
+          const bool own = idx[p] >= kb + (((p & 1) && blk == 0) ? 1 : 0) && idx[p] < kb + R;
           e2[p] = fmaxf(e2[p], own ? eb[p] - ebm[p] : ebm[p]);
         }
-      }
-    }
-  }
-
-  __device__ __forceinline__ void column(float (&acc)[kP], int dy, int blk) {
-    if (dy == P.mid_dy && blk == P.mid_blk) {
-#pragma unroll
-      for (int p = 0; p < kP; ++p) vmid[p * kCThreads] = acc[p];
-    }
-    const int k = dy * P.g.maxw + blk * kR + 1;
-    const int bit = dy * P.g.bs.per_row() + blk;
-    const float rowf = (float)(dy + 1), colf = (float)(blk * kR + 1);
-#pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      if (acc[p] < m[p]) new_min(p, acc[p], k, bit);
-      const float e = ex2_approx((m[p] - acc[p]) * kLog2e);
-      S[p] += e;
-      if (SOFT) {
-        sx[p] = fmaf(e, colf, sx[p]);
-        sy[p] = fmaf(e, rowf, sy[p]);
-      }
-      if (P.nwords && e > P.thr_lo * S[p]) {
-        mask[((bit >> 5) * kP + p) * kCThreads] |= 1u << (bit & 31);
-        if (idx[p] != k) e2[p] = fmaxf(e2[p], e);
       }
     }
   }
@@ -347,10 +335,11 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
         const int id = w * 32 + __ffs(bits) - 1;
         bits &= bits - 1;
         const int dy = id / per_row, blk = id - dy * per_row;
-        const int dxb = blk * kR;
-        const int width = blk >= T.bs.n8 ? 1 : (blk == T.bs.n8 - 1 ? T.bs.last_valid : kR);
+        const int dxb = blk * kR - (x & 1);  // skewed blocks: odd pixels start one column earlier
+        const int width = blk >= T.bs.n8 ? T.bs.tail_r : kR;
+        const bool valid = lane < width && dxb + lane >= 0 && dxb + lane < T.maxw;
         float pk = 0.0f;
-        if (lane < width) {
+        if (valid) {
           const float *b = b0 + dy * T.s2y + dxb + lane;
           float bv[kMaxC];
 #pragma unroll
@@ -364,7 +353,7 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
             }
           pk = expf(m - acc) * inv;
         }
-        unsigned hit = __ballot_sync(0xffffffffu, lane < width && (double)pk > T.thr);
+        unsigned hit = __ballot_sync(0xffffffffu, valid && (double)pk > T.thr);
         while (hit && got < T.M) {
           const int src = __ffs(hit) - 1;
           hit &= hit - 1;
@@ -432,44 +421,38 @@ struct VolumeEpi {
     }
   }
 
-  // stage `nr` displacement rows of 128 pixels, then write rvalid consecutive floats per pixel
-  __device__ __forceinline__ void flush(int dy, int dxb, int rvalid) {
+  // `R` displacement rows of 128 pixels are staged; pixel px owns R consecutive window entries
+  // starting at dx = dxb - (px & 1) (skewed blocks), the ones inside [0, maxw) are written
+  template <int R>
+  __device__ __forceinline__ void flush(int dy, int dxb) {
     const int lane = threadIdx.x & 31;
     const int K = P.g.maxh * P.g.maxw;
     __syncwarp();
-    const int total = npx * rvalid;
-    float *dst = P.out + obase + (size_t)dy * P.g.maxw + dxb;
+    const int total = npx * R;
+    float *dst = P.out + obase + (size_t)dy * P.g.maxw;
     for (int i = lane; i < total; i += 32) {
-      const int px = i / rvalid, r = i - px * rvalid;
-      dst[(size_t)px * K + r] = stg[r * kStgStride + px];
+      const int px = i / R, r = i - px * R;
+      const int dx = dxb - (px & 1) + r;
+      if (dx >= 0 && dx < P.g.maxw) dst[(size_t)px * K + dx] = stg[r * kStgStride + px];
     }
     __syncwarp();
   }
 
-  __device__ __forceinline__ void block(float (&acc)[kP][kR], int dy, int blk, int rvalid) {
+  template <int R>
+  __device__ __forceinline__ void block(float (&acc)[kP][R], int dy, int blk) {
     const int lane = threadIdx.x & 31;
     if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
 #pragma unroll
       for (int p = 0; p < kP; ++p)
 #pragma unroll
-        for (int r = 0; r < kR; ++r)
+        for (int r = 0; r < R; ++r)
           acc[p][r] = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p])) * inv[p];
     }
 #pragma unroll
-    for (int r = 0; r < kR; ++r)
+    for (int r = 0; r < R; ++r)
       *reinterpret_cast<float4 *>(stg + r * kStgStride + lane * kP) =
           make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
-    flush(dy, blk * kR, rvalid);
-  }
-
-  __device__ __forceinline__ void column(float (&acc)[kP], int dy, int blk) {
-    const int lane = threadIdx.x & 31;
-    if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
-#pragma unroll
-      for (int p = 0; p < kP; ++p) acc[p] = ex2_approx(fmaf(acc[p], -kLog2e, mL[p])) * inv[p];
-    }
-    *reinterpret_cast<float4 *>(stg + lane * kP) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    flush(dy, blk * kR, 1);
+    flush<R>(dy, blk * kR);
   }
 
   __device__ __forceinline__ void tile_end(int, int, int) {}
@@ -601,6 +584,17 @@ int generic_match_extract(Call &call, const dm_pair *in, int maxh, int maxw, uns
                           double thr, int h_img, int w_img, const dm_extract_out *out);
 int generic_match_volume(Call &call, const dm_pair *in, int maxh, int maxw, int mode, bool exact,
                          float *out);
+// zero-flow column dx = cx - 1 in the skewed block layout: even pixels dx = 8*blk + r, odd
+// pixels dx = 8*blk - 1 + r
+static void set_middle(ExtractParams *P, int maxw) {
+  const int dx = P->cx - 1;
+  P->mid_blk[0] = dx / kR;
+  P->mid_r[0] = dx % kR;
+  P->mid_blk[1] = (dx + 1) / kR;
+  P->mid_r[1] = (dx + 1) % kR;
+  P->middle = P->mid_dy * maxw + P->cx;
+}
+
 static const void *pick_extract(int CT, bool exact, bool soft) {
 #define DM_PICK(ct)                                                                             \
   (exact ? (soft ? (const void *)match_extract_kernel<ct, true, true>                            \
@@ -660,10 +654,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   P.cy = (maxh + 1) / 2;
   P.cx = (maxw + 1) / 2;
   P.mid_dy = P.cy - 1;
-  P.mid_blk = (P.cx - 1) / kR;
-  P.mid_r = (P.cx - 1) % kR;
-  if (P.mid_blk >= g.bs.n8) P.mid_r = 0;  // the zero-flow column is the trailing single column
-  P.middle = P.mid_dy * maxw + P.cx;
+  set_middle(&P, maxw);
   P.h_img = h_img;
   P.w_img = w_img;
   P.hoff = (h_img - g.H1) / 2;
@@ -817,9 +808,7 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
   P.cy = (g.maxh + 1) / 2;
   P.cx = (g.maxw + 1) / 2;
   P.mid_dy = P.cy - 1;
-  P.mid_blk = (P.cx - 1) / kR;
-  P.mid_r = (P.cx - 1) % kR;
-  P.middle = P.mid_dy * g.maxw + P.cx;
+  set_middle(&P, g.maxw);
   P.min_ssd = vmin;
   P.pmax = vinv;
   const size_t smem = ring_bytes(g) + kBarBytes + (size_t)kCThreads * kP * sizeof(unsigned);

@@ -34,29 +34,28 @@ constexpr int kPrefetch = 8;       // rows in flight beyond the TH the warps are
 constexpr int kNSlot = kTH + kPrefetch;
 constexpr int kMaxC = 16;          // channels supported by the tiled kernels
 
-// Block schedule for a window width: n8 blocks of 8 columns, the last of which has
-// `last_valid` (1..8) real columns, then `single` (0/1) trailing single column.
+// Block schedule for a window width.  Displacements are swept in "skewed" blocks: in block
+// `blk` an even pixel (x even) covers dx = 8*blk + r and an odd pixel dx = 8*blk - 1 + r,
+// r = 0..7, so that the pair (even pixel, r) / (odd pixel, r) reads the SAME frame-2 column
+// and one packed FADD2/FFMA2 with a broadcast operand serves both.  n8 = maxw / 8 full blocks
+// are followed by one tail block (index n8) of `tail_r` columns: 2 when at most two columns
+// are left (maxw % 8 <= 1), else 8.  Entries outside [0, maxw) are masked by the epilogue.
 struct BlockSchedule {
-  int n8, last_valid, single;
-  __host__ __device__ int per_row() const { return n8 + single; }
+  int n8, tail_r;
+  __host__ __device__ int per_row() const { return n8 + 1; }
 };
 __host__ __device__ inline BlockSchedule block_schedule(int maxw) {
   BlockSchedule s;
-  const int rem = maxw % kR;
-  if (rem == 1 && maxw > 1) {
-    s.n8 = maxw / kR;
-    s.last_valid = kR;
-    s.single = 1;
-  } else {
-    s.n8 = (maxw + kR - 1) / kR;
-    s.last_valid = rem ? rem : kR;
-    s.single = 0;
-  }
+  s.n8 = maxw / kR;
+  s.tail_r = (maxw - s.n8 * kR + 1 <= 2) ? 2 : kR;
   return s;
 }
 
-// slab width in floats (multiple of 4): lane 31 reads up to 124 + (n8-1)*8 + 12
-__host__ __device__ inline int slab_width(int maxw) { return kTW + block_schedule(maxw).n8 * kR; }
+// slab width in floats (multiple of 4): lane 31 reads 124 + 8*n8 + (12 or 4)
+__host__ __device__ inline int slab_width(int maxw) {
+  const BlockSchedule s = block_schedule(maxw);
+  return kTW - kP + s.n8 * kR + (s.tail_r == kR ? kNB : kP);
+}
 
 struct SweepGeom {
   int N, C, Cin, H1, W1, H2, W2, maxh, maxw;  // C: channels of the slab box (>= Cin, zero-filled)
@@ -68,26 +67,23 @@ struct SweepGeom {
   long long s1n, s1c, s1y;
 };
 
-template <bool EXACT>
-__device__ __forceinline__ float sq_first(float d) {
-  return EXACT ? __fmul_rn(d, d) : d * d;
-}
-template <bool EXACT>
-__device__ __forceinline__ float sq_acc(float d, float acc) {
-  return EXACT ? __fadd_rn(acc, __fmul_rn(d, d)) : fmaf(d, d, acc);
-}
-
-// One channel-complete SSD block: acc[p][r] = sum_k (a[k][p] - slab[k][p + r])^2.
-// EXACT keeps multiply and add separate (bit-exact with the non-contracting CPU path).
-template <int CT, bool EXACT>
-__device__ __forceinline__ void ssd_block(const float (&a)[CT][kP], const float *bsrc, int WB,
-                                          float (&acc)[kP][kR]) {
+// One channel-complete SSD block in packed fp32 (sm_100 FADD2 / FFMA2 / FMUL2):
+//   acc2[pp][j].x = sum_k (a[k][2pp]   - slab[k][2pp + j])^2     even pixel, dx = 8*blk + j
+//   acc2[pp][j].y = sum_k (a[k][2pp+1] - slab[k][2pp + j])^2     odd pixel,  dx = 8*blk + j - 1
+// EXACT keeps multiply and add separate (bit-exact with the non-contracting CPU path).  ptxas
+// 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit .rn, so the EXACT path
+// packs only the subtraction and squares / accumulates with the scalar __fmul_rn / __fadd_rn,
+// which are never contracted.
+template <int CT, bool EXACT, int JW>
+__device__ __forceinline__ void ssd_block2(const float2 (&a2)[CT][2], const float *bsrc, int WB,
+                                           float2 (&acc2)[2][JW]) {
+  constexpr int NBF = JW == kR ? kNB : kP;
 #pragma unroll
   for (int k = 0; k < CT; ++k) {
-    float b[kNB];
+    float b[NBF];
     const float4 *src = reinterpret_cast<const float4 *>(bsrc + k * WB);
 #pragma unroll
-    for (int j = 0; j < kNB / 4; ++j) {
+    for (int j = 0; j < NBF / 4; ++j) {
       const float4 t = src[j];
       b[4 * j + 0] = t.x;
       b[4 * j + 1] = t.y;
@@ -95,35 +91,37 @@ __device__ __forceinline__ void ssd_block(const float (&a)[CT][kP], const float 
       b[4 * j + 3] = t.w;
     }
 #pragma unroll
-    for (int p = 0; p < kP; ++p)
+    for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-      for (int r = 0; r < kR; ++r) {
-        const float d = a[k][p] - b[p + r];
-        acc[p][r] = k == 0 ? sq_first<EXACT>(d) : sq_acc<EXACT>(d, acc[p][r]);
+      for (int j = 0; j < JW; ++j) {
+        const float nb = -b[2 * pp + j];
+        const float2 d = __fadd2_rn(a2[k][pp], make_float2(nb, nb));
+        if (EXACT) {
+          const float sx = __fmul_rn(d.x, d.x), sy = __fmul_rn(d.y, d.y);
+          acc2[pp][j] = k == 0 ? make_float2(sx, sy)
+                               : make_float2(__fadd_rn(acc2[pp][j].x, sx), __fadd_rn(acc2[pp][j].y, sy));
+        } else {
+          acc2[pp][j] = k == 0 ? __fmul2_rn(d, d) : __ffma2_rn(d, d, acc2[pp][j]);
+        }
       }
   }
 }
 
-// A single displacement column: acc[p] = sum_k (a[k][p] - slab[k][p])^2
-template <int CT, bool EXACT>
-__device__ __forceinline__ void ssd_column(const float (&a)[CT][kP], const float *bsrc, int WB,
-                                           float (&acc)[kP]) {
+template <int JW>
+__device__ __forceinline__ void unpack_block(const float2 (&acc2)[2][JW], float (&acc)[kP][JW]) {
 #pragma unroll
-  for (int k = 0; k < CT; ++k) {
-    const float4 t = *reinterpret_cast<const float4 *>(bsrc + k * WB);
-    const float b[4] = {t.x, t.y, t.z, t.w};
+  for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      const float d = a[k][p] - b[p];
-      acc[p] = k == 0 ? sq_first<EXACT>(d) : sq_acc<EXACT>(d, acc[p]);
+    for (int j = 0; j < JW; ++j) {
+      acc[2 * pp][j] = acc2[pp][j].x;
+      acc[2 * pp + 1][j] = acc2[pp][j].y;
     }
-  }
 }
 
 // Runs the whole sweep for the tiles of this CTA.  `Epi` supplies:
 //   void tile_begin(n, y, x0)                       per tile, after `a` is loaded
-//   void block(acc[kP][8], dy, blk, rvalid)         per (dy, 8-wide dx-block), all threads
-//   void column(acc[kP], dy, blk)                   per (dy, trailing single column)
+//   void block<R>(acc[kP][R], dy, blk)              per (dy, skewed dx-block), R = 8 or 2:
+//                                                   acc[p][r] is dx = 8*blk - (p & 1) + r
 //   void tile_end(n, y, x0)                         per tile
 //
 // Pipeline: rows of all the CTA's tiles form one sequence; row `seq` lives in ring slot
@@ -140,6 +138,7 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGe
   const uint32_t slab_bytes = (uint32_t)(g.C * g.WB * sizeof(float));
   const int slab_floats = g.slab_floats;
   const int n8 = g.bs.n8;
+  const bool wide_tail = g.bs.tail_r == kR;
   uint64_t *full = bars, *empty = bars + kNSlot;
 
   if (threadIdx.x == 0) {
@@ -186,17 +185,20 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGe
     const int y0 = ty * kTH, xt = tx * kTW;
     const int y = y0 + warp, x0 = xt + lane * kP;
 
-    float a[CT][kP];
+    float2 a2[CT][2];
     {
       const bool rowok = y < g.H1;
       const float *src = g.in1 + (long long)n * g.s1n + (long long)(rowok ? y : 0) * g.s1y;
 #pragma unroll
-      for (int k = 0; k < CT; ++k)
+      for (int k = 0; k < CT; ++k) {
+        float a[kP];
 #pragma unroll
         for (int p = 0; p < kP; ++p)
-          a[k][p] = (rowok && k < g.Cin && x0 + p < g.W1)
-                        ? __ldg(src + (long long)k * g.s1c + x0 + p)
-                        : 0.0f;
+          a[p] = (rowok && k < g.Cin && x0 + p < g.W1) ? __ldg(src + (long long)k * g.s1c + x0 + p)
+                                                        : 0.0f;
+        a2[k][0] = make_float2(a[0], a[1]);
+        a2[k][1] = make_float2(a[2], a[3]);
+      }
     }
     epi.tile_begin(n, y, x0);
 
@@ -208,16 +210,21 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGe
       const int dy = j - warp;
       if (dy >= 0 && dy < g.maxh) {
         const float *brow = ring + slot * slab_floats + lane * kP;
+        const int nwide = n8 + (wide_tail ? 1 : 0);
 #pragma unroll 1
-        for (int blk = 0; blk < n8; ++blk) {
+        for (int blk = 0; blk < nwide; ++blk) {
+          float2 acc2[2][kR];
+          ssd_block2<CT, EXACT, kR>(a2, brow + blk * kR, g.WB, acc2);
           float acc[kP][kR];
-          ssd_block<CT, EXACT>(a, brow + blk * kR, g.WB, acc);
-          epi.block(acc, dy, blk, blk == n8 - 1 ? g.bs.last_valid : kR);
+          unpack_block<kR>(acc2, acc);
+          epi.template block<kR>(acc, dy, blk);
         }
-        if (g.bs.single) {
-          float acc[kP];
-          ssd_column<CT, EXACT>(a, brow + n8 * kR, g.WB, acc);
-          epi.column(acc, dy, n8);
+        if (!wide_tail) {
+          float2 acc2[2][2];
+          ssd_block2<CT, EXACT, 2>(a2, brow + n8 * kR, g.WB, acc2);
+          float acc[kP][2];
+          unpack_block<2>(acc2, acc);
+          epi.template block<2>(acc, dy, n8);
         }
       }
       __syncwarp();
