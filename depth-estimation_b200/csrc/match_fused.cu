@@ -53,6 +53,7 @@ struct ExtractParams {
 // Shared memory per pixel: the shortlist bitmap [nwords] and the SSD of the zero-flow entry.
 template <bool SOFT>
 struct ExtractEpi {
+  static constexpr int kCThreads = ExtractCfg::kCThreads;
   const ExtractParams &P;
   float m[kP], S[kP], sx[kP], sy[kP];
   int idx[kP];
@@ -257,14 +258,14 @@ struct ExtractEpi {
 };
 
 template <int CT, bool EXACT, bool SOFT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(ExtractCfg::kThreads, 1)
 match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const ExtractParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ring = reinterpret_cast<float *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kNSlot * P.g.slab_floats);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)ExtractCfg::kNSlot * P.g.slab_floats);
   unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
   ExtractEpi<SOFT> epi(P, extra);
-  run_sweep<CT, EXACT>(&tmap, P.g, ring, full, epi);
+  run_sweep<ExtractCfg, CT, EXACT>(&tmap, P.g, ring, full, epi);
 }
 
 // ---------------------------------------------------------------- exact threshold pass
@@ -388,19 +389,29 @@ struct VolumeParams {
   const float *vmin;   // [N][H1][W1], mode NEG_SOFTMAX: min_k v_k
   const float *vinv;   // [N][H1][W1] 1 / sum_k exp(min - v_k)
   float *out;          // [N][H1][W1][K]
+  int debug;           // DM_VOLUME_DEBUG: 1 = skip the global stores, 2 = stores wrap into 32 MB
 };
 
-constexpr int kStgStride = kTW + 4;  // floats per staged displacement row (bank-conflict-free)
+// Store staging of the volume kernel.  The output tensor [px][K] gives every pixel a
+// contiguous stream of K floats, K*4 bytes is in general not a multiple of the 32-byte DRAM
+// sector, and a (pixel, block) produces only 8 stream entries: storing them as they come
+// touches two partial sectors per run, and B200's L2 fills partially written sectors from
+// DRAM (measured: +60 % reads, +47 % writes, 0.9 TB/s).  So each pixel's stream goes through a
+// 16-entry circular buffer in shared memory (index = stream position mod 16) and leaves as
+// whole, 32-byte-aligned sectors: after every block at most one sector per pixel completes, 8
+// lanes write it.  Only the first and last sector of a pixel's stream (shared with the
+// neighbouring pixels) are written partially.
+constexpr int kStgPlane = 16 * 66;  // one parity plane: [16 positions][64 pixels + 2 pad]
 
 struct VolumeEpi {
   const VolumeParams &P;
-  float *stg;  // this warp's staging area: [kR][kStgStride]
+  float *stg;  // this warp's staging: plane 0 even pixels, plane 1 odd pixels
   float mL[kP], inv[kP];
-  size_t obase;  // output offset of (n, y, tile x)
+  size_t obase;  // stream offset (floats) of pixel 0 of this warp's row in the tile
   int npx;       // valid pixels of this warp's row in the tile
 
   __device__ VolumeEpi(const VolumeParams &p, float *stg_all)
-      : P(p), stg(stg_all + (threadIdx.x >> 5) * (kR * kStgStride)) {}
+      : P(p), stg(stg_all + (threadIdx.x >> 5) * (2 * kStgPlane)) {}
 
   __device__ __forceinline__ void tile_begin(int n, int y, int x0) {
     const SweepGeom &g = P.g;
@@ -421,26 +432,11 @@ struct VolumeEpi {
     }
   }
 
-  // `R` displacement rows of 128 pixels are staged; pixel px owns R consecutive window entries
-  // starting at dx = dxb - (px & 1) (skewed blocks), the ones inside [0, maxw) are written
-  template <int R>
-  __device__ __forceinline__ void flush(int dy, int dxb) {
-    const int lane = threadIdx.x & 31;
-    const int K = P.g.maxh * P.g.maxw;
-    __syncwarp();
-    const int total = npx * R;
-    float *dst = P.out + obase + (size_t)dy * P.g.maxw;
-    for (int i = lane; i < total; i += 32) {
-      const int px = i / R, r = i - px * R;
-      const int dx = dxb - (px & 1) + r;
-      if (dx >= 0 && dx < P.g.maxw) dst[(size_t)px * K + dx] = stg[r * kStgStride + px];
-    }
-    __syncwarp();
-  }
-
+  // acc[p][r] is window entry dx = 8*blk - (p & 1) + r of pixel p (skewed blocks)
   template <int R>
   __device__ __forceinline__ void block(float (&acc)[kP][R], int dy, int blk) {
     const int lane = threadIdx.x & 31;
+    const int maxw = P.g.maxw, K = P.g.maxh * maxw;
     if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
 #pragma unroll
       for (int p = 0; p < kP; ++p)
@@ -448,29 +444,108 @@ struct VolumeEpi {
         for (int r = 0; r < R; ++r)
           acc[p][r] = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p])) * inv[p];
     }
+    // 1. stage: stream index q = dy*maxw + dx -> position q & 15, pixel pairs (0,2) and (1,3)
+    const int q0 = dy * maxw + blk * kR;  // stream index of (even pixel, r = 0)
+    __syncwarp();
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      *reinterpret_cast<float4 *>(stg + r * kStgStride + lane * kP) =
-          make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
-    flush<R>(dy, blk * kR);
+    for (int r = 0; r < R; ++r) {
+      const int dxe = blk * kR + r, dxo = dxe - 1;
+      if (dxe < maxw)
+        *reinterpret_cast<float2 *>(stg + ((q0 + r) & 15) * 66 + 2 * lane) =
+            make_float2(acc[0][r], acc[2][r]);
+      if (dxo >= 0 && dxo < maxw)
+        *reinterpret_cast<float2 *>(stg + kStgPlane + ((q0 + r - 1) & 15) * 66 + 2 * lane) =
+            make_float2(acc[1][r], acc[3][r]);
+    }
+    __syncwarp();
+    // 2. flush the sectors this block completed
+    if (P.debug == 1) return;
+    const long long s_even = (long long)dy * maxw + min(blk * kR + R, maxw);
+    const bool ends = dy == P.g.maxh - 1 && blk * kR + R - 1 >= maxw;  // a pixel stream may end here
+    if (s_even >= 24 && !ends)
+      flush_fast<R>(dy, blk);
+    else
+      flush_edges<R>(dy, blk);
+  }
+
+  // Steady state: every completed sector lies fully inside its pixel's stream.  Two lanes per
+  // sector (16 bytes each, one STG.128), 16 pixels per iteration.  Advancing 16 pixels moves the
+  // stream start by 16*K floats, a multiple of the sector, so the lane's alignment phase, the
+  // staging rows it reads and "did a sector complete" are fixed for the whole block.
+  template <int R>
+  __device__ __forceinline__ void flush_fast(int dy, int blk) {
+    const int lane = threadIdx.x & 31;
+    const int maxw = P.g.maxw, K = P.g.maxh * maxw;
+    const int pxl = lane >> 1, h = lane & 1, par = pxl & 1;
+    const int lo = max(blk * kR - par, 0), hi = min(blk * kR - par + R, maxw);
+    const int nvalid = hi - lo;
+    const int s_end = dy * maxw + hi;
+    const int phase = (int)((obase + (size_t)pxl * K) & 7);
+    const int u = (phase + s_end) & 7;       // floats of the still incomplete sector
+    if (u >= nvalid) return;                 // no sector completed for this lane's pixels
+    const int qs = s_end - u - 8 + 4 * h;    // stream index of this lane's 4 floats
+    const float *src = stg + par * kStgPlane + (pxl >> 1);
+    const int r0 = ((qs + 0) & 15) * 66, r1 = ((qs + 1) & 15) * 66, r2 = ((qs + 2) & 15) * 66,
+              r3 = ((qs + 3) & 15) * 66;
+    float *dst = P.out + obase + (size_t)pxl * K + qs;
+    const size_t step = (size_t)16 * K;
+#pragma unroll
+    for (int it = 0; it < kTW / 16; ++it) {
+      const float4 v = make_float4(src[r0 + 8 * it], src[r1 + 8 * it], src[r2 + 8 * it], src[r3 + 8 * it]);
+      if (16 * it + pxl < npx) *reinterpret_cast<float4 *>(dst + it * step) = v;
+    }
+  }
+
+  // First and last sectors of a pixel's stream are shared with the neighbouring pixels:
+  // scalar stores, 8 lanes per sector, floats outside the stream masked.
+  template <int R>
+  __device__ __forceinline__ void flush_edges(int dy, int blk) {
+    const int lane = threadIdx.x & 31;
+    const int maxw = P.g.maxw, K = P.g.maxh * maxw;
+    const int g4 = lane >> 3, i = lane & 7, par = g4 & 1;
+    const int lo = max(blk * kR - par, 0), hi = min(blk * kR - par + R, maxw);
+    const int nvalid = hi - lo;
+    const long long s_end = (long long)dy * maxw + hi;  // stream index after this block
+    const bool last = dy == P.g.maxh - 1 && hi == maxw;  // the pixel's stream ends here
+    const float *src = stg + par * kStgPlane + (g4 >> 1);
+    float *out = P.out;
+#pragma unroll 4
+    for (int it = 0; it < kTW / 4; ++it) {
+      const int px = 4 * it + g4;
+      const long long base = (long long)obase + (long long)px * K;  // stream start of the pixel
+      const long long G = base + s_end - nvalid, Gend = base + s_end;
+      const long long E = Gend & ~7LL;  // end of the last complete sector
+      if (px < npx && nvalid > 0) {
+        if (E > G) {  // sector [E-8, E) completed (floats before `base` are the previous pixel's)
+          const long long f = E - 8 + i;
+          if (f >= base) out[f] = src[(int)((f - base) & 15) * 66 + 2 * it];
+        }
+        if (last && i < (int)(Gend - E)) {
+          const long long f = E + i;
+          out[f] = src[(int)((f - base) & 15) * 66 + 2 * it];
+        }
+      }
+    }
   }
 
   __device__ __forceinline__ void tile_end(int, int, int) {}
 };
 
 template <int CT, bool EXACT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(VolumeCfg::kThreads, 1)
 match_volume_kernel(const __grid_constant__ CUtensorMap tmap, const VolumeParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ring = reinterpret_cast<float *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kNSlot * P.g.slab_floats);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)VolumeCfg::kNSlot * P.g.slab_floats);
   float *stg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
   VolumeEpi epi(P, stg);
-  run_sweep<CT, EXACT>(&tmap, P.g, ring, full, epi);
+  run_sweep<VolumeCfg, CT, EXACT>(&tmap, P.g, ring, full, epi);
 }
 
 // ---------------------------------------------------------------- host side
-static size_t ring_bytes(const SweepGeom &g) { return (size_t)kNSlot * g.slab_floats * sizeof(float); }
+static size_t ring_bytes(const SweepGeom &g, int nslot) {
+  return (size_t)nslot * g.slab_floats * sizeof(float);
+}
 
 struct Prepared {
   SweepGeom g;
@@ -486,7 +561,7 @@ struct Prepared {
 // build the tensor map of frame 2: dims {W2, H2, C, N}, box {WB, 1, CT, 1}.  The
 // channel dim of the box is CT >= C: TMA zero-fills the missing channels and the
 // kernel keeps a = 0 for them, so they add exactly 0 to every SSD.
-static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, Prepared *out) {
+static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, int tile_rows, Prepared *out) {
   dm_ctx *ctx = call.ctx;
   DM_REQUIRE(in && in->in1 && in->in2, "input pointers are NULL");
   DM_REQUIRE(in->n_pairs >= 1 && in->channels >= 1, "n_pairs and channels must be >= 1");
@@ -508,7 +583,7 @@ static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, Prepared *
   g.bs = block_schedule(maxw);
   g.WB = slab_width(maxw);
   g.tiles_x = (g.W1 + kTW - 1) / kTW;
-  g.tiles_y = (g.H1 + kTH - 1) / kTH;
+  g.tiles_y = (g.H1 + tile_rows - 1) / tile_rows;
   g.ntiles = g.tiles_x * g.tiles_y * g.N;
   out->CT = g.C <= 4 ? 4 : (g.C <= 10 ? 10 : 16);
 
@@ -605,9 +680,9 @@ static const void *pick_extract(int CT, bool exact, bool soft) {
 #undef DM_PICK
 }
 
-static int grid_for(dm_ctx *ctx, const void *kernel, size_t smem, int ntiles) {
+static int grid_for(dm_ctx *ctx, const void *kernel, int threads, size_t smem, int ntiles) {
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) {
     cudaGetLastError();
     per_sm = 1;
   }
@@ -638,7 +713,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     return rc != DM_OK ? rc : rf;
   }
   Prepared pr;
-  DM_CHECK(prepare(call, in, maxh, maxw, &pr));
+  DM_CHECK(prepare(call, in, maxh, maxw, ExtractCfg::kTH, &pr));
   const SweepGeom &g = pr.g;
   const size_t npx = (size_t)g.N * g.H1 * g.W1;
 
@@ -701,17 +776,18 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     P.vinv = P.vmin + npx;
     DM_CUDA(cudaMemsetAsync(P.ntodo, 0, sizeof(unsigned), ctx->stream));
   }
-  const size_t smem = ring_bytes(g) + kBarBytes + (size_t)(P.nwords + 1) * kCThreads * kP * sizeof(unsigned);
+  const size_t smem = ring_bytes(g, ExtractCfg::kNSlot) + kBarBytes +
+                      (size_t)(P.nwords + 1) * ExtractCfg::kCThreads * kP * sizeof(unsigned);
   DM_REQUIRE(smem <= ctx->smem_optin, "window %dx%d with %d channels needs %zu bytes of shared memory",
              maxh, maxw, g.C, smem);
   const bool exact = flags & DM_FLAG_EXACT_SSD;
   const void *kfn = nullptr;
   kfn = pick_extract(pr.CT, exact, P.soft_yx != nullptr);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = grid_for(ctx, kfn, smem, g.ntiles);
+  const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&P};
   prof_begin(ctx);
-  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(ExtractCfg::kThreads), args, smem, ctx->stream));
   prof_end(ctx);
   count_launch(ctx);
   if (want_thr) {
@@ -811,12 +887,13 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
   set_middle(&P, g.maxw);
   P.min_ssd = vmin;
   P.pmax = vinv;
-  const size_t smem = ring_bytes(g) + kBarBytes + (size_t)kCThreads * kP * sizeof(unsigned);
+  const size_t smem = ring_bytes(g, ExtractCfg::kNSlot) + kBarBytes +
+                      (size_t)ExtractCfg::kCThreads * kP * sizeof(unsigned);
   const void *kfn = pick_extract(pr.CT, exact, false);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = grid_for(ctx, kfn, smem, g.ntiles);
+  const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&P};
-  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(ExtractCfg::kThreads), args, smem, ctx->stream));
   count_launch(ctx);
   return DM_OK;
 }
@@ -838,7 +915,7 @@ extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int max
     return rc != DM_OK ? rc : rf;
   }
   Prepared pr;
-  DM_CHECK(prepare(call, in, maxh, maxw, &pr));
+  DM_CHECK(prepare(call, in, maxh, maxw, VolumeCfg::kTH, &pr));
   const SweepGeom &g = pr.g;
   const size_t npx = (size_t)g.N * g.H1 * g.W1;
   const size_t K = (size_t)maxh * maxw;
@@ -849,16 +926,20 @@ extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int max
   P.mode = mode;
   P.vmin = P.vinv = nullptr;
   P.out = static_cast<float *>(p);
+  P.debug = getenv("DM_VOLUME_DEBUG") ? atoi(getenv("DM_VOLUME_DEBUG")) : 0;
   if (mode == DM_VOLUME_NEG_SOFTMAX) {
     void *s = nullptr;
     DM_CHECK(call.alloc(&s, npx * 2 * sizeof(float)));
     float *vmin = static_cast<float *>(s), *vinv = vmin + npx;
-    DM_CHECK(launch_stats(call, pr, exact, vmin, vinv));
+    Prepared ps = pr;  // the statistics sweep runs with the extraction kernel's tile height
+    ps.g.tiles_y = (g.H1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH;
+    ps.g.ntiles = ps.g.tiles_x * ps.g.tiles_y * g.N;
+    DM_CHECK(launch_stats(call, ps, exact, vmin, vinv));
     P.vmin = vmin;
     P.vinv = vinv;
   }
-  const size_t smem = ring_bytes(g) + kBarBytes +
-                      (size_t)kWarps * kR * kStgStride * sizeof(float);
+  const size_t smem = ring_bytes(g, VolumeCfg::kNSlot) + kBarBytes +
+                      (size_t)VolumeCfg::kWarps * 2 * kStgPlane * sizeof(float);
   DM_REQUIRE(smem <= ctx->smem_optin, "window %dx%d with %d channels needs %zu bytes of shared memory",
              maxh, maxw, g.C, smem);
 #define DM_PICKV(ct)                                                                  \
@@ -866,10 +947,10 @@ extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int max
   const void *kfn = pr.CT == 4 ? DM_PICKV(4) : (pr.CT == 10 ? DM_PICKV(10) : DM_PICKV(16));
 #undef DM_PICKV
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = grid_for(ctx, kfn, smem, g.ntiles);
+  const int grid = grid_for(ctx, kfn, VolumeCfg::kThreads, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&P};
   prof_begin(ctx);
-  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(VolumeCfg::kThreads), args, smem, ctx->stream));
   prof_end(ctx);
   count_launch(ctx);
   return call.finish();

@@ -23,16 +23,23 @@
 namespace dm {
 
 constexpr int kP = 4;              // pixels per thread
-constexpr int kWarps = 15;         // consumer warps = output rows per tile (one per warp)
-constexpr int kCThreads = kWarps * 32;    // consumer threads
-constexpr int kThreads = kCThreads + 32;  // + one producer warp that issues the TMA loads
 constexpr int kTW = 32 * kP;       // 128 output columns per tile
-constexpr int kTH = kWarps;
 constexpr int kR = 8;              // displacement block width
 constexpr int kNB = 12;            // floats of the slab a thread reads per channel (3 x float4)
-constexpr int kPrefetch = 8;       // rows in flight beyond the TH the warps are reading
-constexpr int kNSlot = kTH + kPrefetch;
 constexpr int kMaxC = 16;          // channels supported by the tiled kernels
+
+// CTA shape of a sweep kernel: NW consumer warps (= output rows per tile, one per warp) plus
+// one producer warp; PF rows in flight beyond the NW the warps are reading.
+template <int NW, int PF>
+struct SweepCfg {
+  static constexpr int kWarps = NW;
+  static constexpr int kCThreads = NW * 32;        // consumer threads
+  static constexpr int kThreads = kCThreads + 32;  // + the TMA producer warp
+  static constexpr int kTH = NW;
+  static constexpr int kNSlot = NW + PF;
+};
+using ExtractCfg = SweepCfg<15, 8>;  // fused extraction: registers allow 16 warps of 128
+using VolumeCfg = SweepCfg<12, 4>;   // volume output: leaves shared memory for the store staging
 
 // Block schedule for a window width.  Displacements are swept in "skewed" blocks: in block
 // `blk` an even pixel (x even) covers dx = 8*blk + r and an odd pixel dx = 8*blk - 1 + r,
@@ -130,9 +137,10 @@ __device__ __forceinline__ void unpack_block(const float2 (&acc2)[2][JW], float 
 // completes full[slot].  Every consumer warp walks every row of its tile in order: wait
 // full, compute if the row is inside its own window (row - warp in [0, maxh)), release.
 // No CTA-wide barrier: warps drift apart by up to NSLOT - TH rows, across tile borders too.
-template <int CT, bool EXACT, class Epi>
+template <class Cfg, int CT, bool EXACT, class Epi>
 __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGeom &g, float *ring,
                                           uint64_t *bars, Epi &epi) {
+  constexpr int kWarps = Cfg::kWarps, kTH = Cfg::kTH, kNSlot = Cfg::kNSlot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_total = kTH + g.maxh - 1;
   const uint32_t slab_bytes = (uint32_t)(g.C * g.WB * sizeof(float));
