@@ -222,8 +222,15 @@ def main():
     in1 = crop(f1)
     want = ("index", "pmax", "score_thr")
 
+    # result buffers are allocated once: a cudaMalloc inside the timed region (torch's caching
+    # allocator growing when two result sets are alive) would stall the device for milliseconds
+    out_d = {"index": torch.empty((B, H1, W1), dtype=torch.int64, device="cuda"),
+             "pmax": torch.empty((B, H1, W1), device="cuda"),
+             "score_thr": torch.empty((B, H1, W1), device="cuda"),
+             "flow_full": torch.empty((B, 2, H, W), device="cuda")}
+
     def step():
-        return dm.match_extract(in1, f2, MAXH, MAXW, canvas=(H, W), want=want, ctx=ctx)
+        return dm.match_extract(in1, f2, MAXH, MAXW, canvas=(H, W), want=want, ctx=ctx, out=out_d)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
