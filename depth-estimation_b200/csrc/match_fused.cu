@@ -308,15 +308,18 @@ struct ThresholdPass {
   unsigned long long *n_untouched;
 };
 
-// Exact extractOutput for the pixels the sweep could not decide: one warp per pixel walks the
-// pixel's shortlist of (dy, dx-block)s in scan order, recomputes those SSDs with the same
-// arithmetic as the sweep (all channel loads of a block issued before the first use, so a
-// block costs one memory latency), and applies extract_output.cpp:63-155 literally.
+// Exact extractOutput for the pixels the sweep could not decide: eight lanes per pixel (a
+// block is at most 8 entries wide), four pixels per warp in flight.  A group walks its
+// pixel's shortlist of (dy, dx-block)s in scan order, recomputes those SSDs with the sweep's
+// arithmetic (all channel loads of a block issued before the first use, so a block costs one
+// memory latency), and applies extract_output.cpp:63-155 literally.
 __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPass T) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const unsigned gmask = 0xffu << (8 * grp);
   const unsigned n = *T.ntodo;
   const int per_row = T.bs.per_row();
-  for (unsigned e = blockIdx.x * 4 + (threadIdx.x >> 5); e < n; e += gridDim.x * 4) {
+  const unsigned ngroups = gridDim.x * 16;
+  for (unsigned e = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 + grp; e < n; e += ngroups) {
     const long long px = T.todo[e];
     const int x = (int)(px % T.W1), y = (int)((px / T.W1) % T.H1);
     const int pn = (int)(px / ((long long)T.W1 * T.H1));
@@ -338,10 +341,10 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
         const int dy = id / per_row, blk = id - dy * per_row;
         const int dxb = blk * kR - (x & 1);  // skewed blocks: odd pixels start one column earlier
         const int width = blk >= T.bs.n8 ? T.bs.tail_r : kR;
-        const bool valid = lane < width && dxb + lane >= 0 && dxb + lane < T.maxw;
+        const bool valid = gl < width && dxb + gl >= 0 && dxb + gl < T.maxw;
         float pk = 0.0f;
         if (valid) {
-          const float *b = b0 + dy * T.s2y + dxb + lane;
+          const float *b = b0 + dy * T.s2y + dxb + gl;
           float bv[kMaxC];
 #pragma unroll
           for (int c = 0; c < kMaxC; ++c) bv[c] = c < T.C ? __ldg(b + c * T.s2c) : 0.0f;
@@ -354,11 +357,11 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
             }
           pk = expf(m - acc) * inv;
         }
-        unsigned hit = __ballot_sync(0xffffffffu, valid && (double)pk > T.thr);
+        unsigned hit = (__ballot_sync(gmask, valid && (double)pk > T.thr) >> (8 * grp)) & 0xffu;
         while (hit && got < T.M) {
           const int src = __ffs(hit) - 1;
           hit &= hit - 1;
-          const float pv = __shfl_sync(0xffffffffu, pk, src);
+          const float pv = __shfl_sync(gmask, pk, 8 * grp + src);
           const float pp = (float)(dy * T.maxw + dxb + src + 1);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
         }
       }
     }
-    if (lane != 0) continue;
+    if (gl != 0) continue;
     long long ret = 0;
     float score = 0.0f;
     if (got > 0)
