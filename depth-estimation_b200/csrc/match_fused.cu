@@ -41,6 +41,7 @@ struct ExtractParams {
   unsigned long long *n_untouched;
   // thresholded extraction (extractOutput on the probabilities), see ExtractEpi::tile_end
   int nwords;           // 32-bit words of the per-pixel (dy, dx-block) shortlist bitmap
+  int gb;               // consecutive blocks that share one shortlist bit (1 unless the window is huge)
   int *todo;            // pixels that need the exact pass over their shortlist
   unsigned *todo_mask;  // [todo slot][nwords]
   unsigned *ntodo;
@@ -128,7 +129,8 @@ struct ExtractEpi {
     }
     float bm[kP];
     bool any = false;
-    const int bit = dy * P.g.bs.per_row() + blk;
+    const int blkid = dy * P.g.bs.per_row() + blk;
+    const int bit = P.gb == 1 ? blkid : blkid / P.gb;
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
       bm[p] = acc[p][0];
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(ExtractCfg::kThreads, 1)
 match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const ExtractParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ring = reinterpret_cast<float *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)ExtractCfg::kNSlot * P.g.slab_floats);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)P.g.nslot * P.g.slab_floats);
   unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
   ExtractEpi<SOFT> epi(P, extra);
   run_sweep<ExtractCfg, CT, EXACT>(&tmap, P.g, ring, full, epi);
@@ -297,7 +299,7 @@ __device__ inline void net_sort_score(float *val, float *pos, int M, long long *
 struct ThresholdPass {
   const float *in1, *in2;
   long long s1n, s1c, s1y, s2n, s2c, s2y;
-  int N, C, H1, W1, maxh, maxw, nwords, M, exact;
+  int N, C, H1, W1, maxh, maxw, nwords, gb, M, exact;
   BlockSchedule bs;
   double thr;
   const int *todo;
@@ -336,8 +338,9 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
     for (int w = 0; w < T.nwords && got < T.M; ++w) {
       unsigned bits = T.todo_mask[(size_t)e * T.nwords + w];
       while (bits && got < T.M) {
-        const int id = w * 32 + __ffs(bits) - 1;
+        const int bitid = w * 32 + __ffs(bits) - 1;
         bits &= bits - 1;
+       for (int id = bitid * T.gb; id < (bitid + 1) * T.gb && id < T.maxh * per_row && got < T.M; ++id) {
         const int dy = id / per_row, blk = id - dy * per_row;
         const int dxb = blk * kR - (x & 1);  // skewed blocks: odd pixels start one column earlier
         const int width = blk >= T.bs.n8 ? T.bs.tail_r : kR;
@@ -371,6 +374,7 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
             }
           ++got;
         }
+       }
       }
     }
     if (gl != 0) continue;
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(VolumeCfg::kThreads, 1)
 match_volume_kernel(const __grid_constant__ CUtensorMap tmap, const VolumeParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ring = reinterpret_cast<float *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)VolumeCfg::kNSlot * P.g.slab_floats);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)P.g.nslot * P.g.slab_floats);
   float *stg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
   VolumeEpi epi(P, stg);
   run_sweep<VolumeCfg, CT, EXACT>(&tmap, P.g, ring, full, epi);
@@ -673,6 +677,21 @@ static void set_middle(ExtractParams *P, int maxw) {
   P->middle = P->mid_dy * maxw + P->cx;
 }
 
+// ring depth: as many slots as fit next to `extra` bytes, at most the configuration's, at
+// least two more than the tile height (so that the producer can run ahead of the warps)
+static int fit_ring(dm_ctx *ctx, SweepGeom *g, int tile_rows, int max_slots, size_t extra) {
+  const size_t slab = (size_t)g->slab_floats * sizeof(float);
+  long long n = ((long long)ctx->smem_optin - (long long)extra) / (long long)slab;
+  if (n > max_slots) n = max_slots;
+  if (n < tile_rows + 2) {
+    set_error("window %dx%d with %d channels does not fit in shared memory (%zu-byte row slabs)",
+              g->maxh, g->maxw, g->Cin, slab);
+    return DM_ERR_UNSUPPORTED;
+  }
+  g->nslot = (int)n;
+  return DM_OK;
+}
+
 static const void *pick_extract(int CT, bool exact, bool soft) {
 #define DM_PICK(ct)                                                                             \
   (exact ? (soft ? (const void *)match_extract_kernel<ct, true, true>                            \
@@ -763,13 +782,16 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     DM_CUDA(cudaMemsetAsync(P.flow_full, 0, (size_t)g.N * 2 * h_img * w_img * 4, ctx->stream));
 
   P.nwords = 0;
+  P.gb = 1;
   P.todo = nullptr;
   P.todo_mask = nullptr;
   P.ntodo = nullptr;
   P.vmin = P.vinv = nullptr;
   if (want_thr) {
     // one shortlist bit per (dy, dx-block); S >= 1 so p_k > thr needs v_k < min + ln(1/thr)
-    P.nwords = (maxh * g.bs.per_row() + 31) / 32;
+    const int nblocks = maxh * g.bs.per_row();
+    P.gb = (nblocks + 191) / 192;  // at most 6 bitmap words per pixel
+    P.nwords = ((nblocks + P.gb - 1) / P.gb + 31) / 32;
     void *scratch = nullptr;
     DM_CHECK(call.alloc(&scratch, 256 + npx * sizeof(int) * (1 + (size_t)P.nwords) + npx * 8));
     P.ntodo = static_cast<unsigned *>(scratch);
@@ -779,10 +801,9 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     P.vinv = P.vmin + npx;
     DM_CUDA(cudaMemsetAsync(P.ntodo, 0, sizeof(unsigned), ctx->stream));
   }
-  const size_t smem = ring_bytes(g, ExtractCfg::kNSlot) + kBarBytes +
-                      (size_t)(P.nwords + 1) * ExtractCfg::kCThreads * kP * sizeof(unsigned);
-  DM_REQUIRE(smem <= ctx->smem_optin, "window %dx%d with %d channels needs %zu bytes of shared memory",
-             maxh, maxw, g.C, smem);
+  const size_t extra = kBarBytes + (size_t)(P.nwords + 1) * ExtractCfg::kCThreads * kP * sizeof(unsigned);
+  DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
+  const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
   const bool exact = flags & DM_FLAG_EXACT_SSD;
   const void *kfn = nullptr;
   kfn = pick_extract(pr.CT, exact, P.soft_yx != nullptr);
@@ -798,7 +819,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     T.in1 = g.in1; T.s1n = g.s1n; T.s1c = g.s1c; T.s1y = g.s1y;
     T.in2 = pr.in2_dev; T.s2n = pr.s2n; T.s2c = pr.s2c; T.s2y = pr.s2y;
     T.N = g.N; T.C = pr.Cin; T.H1 = g.H1; T.W1 = g.W1; T.maxh = maxh; T.maxw = maxw;
-    T.bs = g.bs; T.nwords = P.nwords; T.M = P.M; T.exact = exact ? 1 : 0;
+    T.bs = g.bs; T.nwords = P.nwords; T.gb = P.gb; T.M = P.M; T.exact = exact ? 1 : 0;
     T.thr = prob_threshold;
     T.todo = P.todo; T.todo_mask = P.todo_mask; T.ntodo = P.ntodo;
     T.vmin = P.vmin; T.vinv = P.vinv;
@@ -890,8 +911,9 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
   set_middle(&P, g.maxw);
   P.min_ssd = vmin;
   P.pmax = vinv;
-  const size_t smem = ring_bytes(g, ExtractCfg::kNSlot) + kBarBytes +
-                      (size_t)ExtractCfg::kCThreads * kP * sizeof(unsigned);
+  const size_t extra = kBarBytes + (size_t)ExtractCfg::kCThreads * kP * sizeof(unsigned);
+  DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
+  const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
   const void *kfn = pick_extract(pr.CT, exact, false);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, g.ntiles);
@@ -941,10 +963,9 @@ extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int max
     P.vmin = vmin;
     P.vinv = vinv;
   }
-  const size_t smem = ring_bytes(g, VolumeCfg::kNSlot) + kBarBytes +
-                      (size_t)VolumeCfg::kWarps * 2 * kStgPlane * sizeof(float);
-  DM_REQUIRE(smem <= ctx->smem_optin, "window %dx%d with %d channels needs %zu bytes of shared memory",
-             maxh, maxw, g.C, smem);
+  const size_t extra = kBarBytes + (size_t)VolumeCfg::kWarps * 2 * kStgPlane * sizeof(float);
+  DM_CHECK(fit_ring(ctx, &P.g, VolumeCfg::kTH, VolumeCfg::kNSlot, extra));
+  const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
 #define DM_PICKV(ct)                                                                  \
   (exact ? (const void *)match_volume_kernel<ct, true> : (const void *)match_volume_kernel<ct, false>)
   const void *kfn = pr.CT == 4 ? DM_PICKV(4) : (pr.CT == 10 ? DM_PICKV(10) : DM_PICKV(16));

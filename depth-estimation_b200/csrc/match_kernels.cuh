@@ -70,6 +70,7 @@ struct SweepGeom {
   int WB;
   BlockSchedule bs;
   int slab_floats;  // floats between ring slots: C*WB rounded up to 128 bytes
+  int nslot;        // ring slots actually used (<= Cfg::kNSlot, >= Cfg::kTH + 2): what fits
   const float *in1;
   long long s1n, s1c, s1y;
 };
@@ -140,14 +141,15 @@ __device__ __forceinline__ void unpack_block(const float2 (&acc2)[2][JW], float 
 template <class Cfg, int CT, bool EXACT, class Epi>
 __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGeom &g, float *ring,
                                           uint64_t *bars, Epi &epi) {
-  constexpr int kWarps = Cfg::kWarps, kTH = Cfg::kTH, kNSlot = Cfg::kNSlot;
+  constexpr int kWarps = Cfg::kWarps, kTH = Cfg::kTH;
+  const int kNSlot = g.nslot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_total = kTH + g.maxh - 1;
   const uint32_t slab_bytes = (uint32_t)(g.C * g.WB * sizeof(float));
   const int slab_floats = g.slab_floats;
   const int n8 = g.bs.n8;
   const bool wide_tail = g.bs.tail_r == kR;
-  uint64_t *full = bars, *empty = bars + kNSlot;
+  uint64_t *full = bars, *empty = bars + Cfg::kNSlot;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(tmap);

@@ -418,3 +418,136 @@ def test_pipelined_host_batch_matches_single_calls(dm):
         one = dm.match_extract(view[n], f2[n], maxh, maxw, canvas=(40, 72), want=want)
         for k in one:
             np.testing.assert_array_equal(batch[k][n], one[k], err_msg=k)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configurations at FULL size.  The oracle needs seconds to minutes per pair at
+# these sizes, so these check size-independent properties (planted integer flow recovered,
+# band partition == whole frame, zero-flow fixed point, idempotence) instead of the volume.
+# ---------------------------------------------------------------------------------------------
+def test_c2_batch64_320x180_planted_flow(dm):
+    """configs[1]: synthetic 320x180 frame pairs, batch 64, single-scale 33x33 window."""
+    import torch
+    maxh = maxw = 33
+    N = 64
+    base = [make_pair(10, 180, 320, maxh, maxw, seed=100 + n, noise=0.05, flow_seed=200 + n) for n in range(4)]
+    in1 = torch.from_numpy(np.stack([base[n % 4][0] for n in range(N)])).cuda()
+    in2 = torch.from_numpy(np.stack([base[n % 4][1] for n in range(N)])).cuda()
+    got = dm.match_extract(in1, in2, maxh, maxw, want=("index", "pmax", "score_thr"))
+    torch.cuda.synchronize()
+    idx = got["index"].cpu().numpy()
+    for n in range(N):
+        flow = base[n % 4][2]
+        np.testing.assert_array_equal((idx[n] - 1) // maxw - 16, flow[0])
+        np.testing.assert_array_equal((idx[n] - 1) % maxw - 16, flow[1])
+    # identical pairs in the batch give identical results (no cross-pair state)
+    for k in ("index", "pmax", "score_thr"):
+        v = got[k].cpu().numpy()
+        np.testing.assert_array_equal(v[0], v[4])
+        np.testing.assert_array_equal(v[3], v[63])
+
+
+def test_c5_1080p_65x65_row_bands_equal_whole_frame(dm):
+    """configs[4]: 1920x1080, 65x65 window, 8 row bands with a 64-row halo: each band
+    computed on its own (what a rank does) must reproduce the whole-frame result exactly."""
+    import torch
+    from depthmatch import parallel
+    maxh = maxw = 65
+    C, H, W = 10, 1080, 1920
+    g = torch.Generator(device="cuda").manual_seed(5)
+    in2 = torch.randn((C, H, W), device="cuda", generator=g)
+    H1, W1 = H - maxh + 1, W - maxw + 1
+    fy, fx = 7, -11   # planted constant flow
+    in1 = in2[:, 32 + fy:32 + fy + H1, 32 + fx:32 + fx + W1] + 0.05 * torch.randn((C, H1, W1), device="cuda", generator=g)
+    whole = dm.match_extract(in1, in2, maxh, maxw, want=("index", "pmax", "score_thr"))
+    idx = whole["index"]
+    assert bool(((idx - 1) // maxw - 32 == fy).all()) and bool(((idx - 1) % maxw - 32 == fx).all())
+    bands = parallel.row_bands(H1, 8, maxh)
+    assert bands[0] == (0, 127, 127 + 64) and bands[-1][1] == H1
+    for rank in (0, 3, 7):
+        a, b = parallel.band_inputs(in1, in2, bands[rank])
+        part = dm.match_extract(a, b, maxh, maxw, want=("index", "pmax", "score_thr"))
+        y0, y1, _ = bands[rank]
+        for k in ("index", "pmax", "score_thr"):
+            assert torch.equal(part[k], whole[k][y0:y1]), (rank, k)
+
+
+def test_c3_multiscale_640x360_properties(dm):
+    """configs[2]: 3 scales {1,2,4}, 8x8 windows, 640x360.  Identical frames -> every pixel picks
+    the zero-flow middle index 28; a frame shifted by (dy,dx) = (-2, 3) within the fine window is
+    decoded back to that flow at full resolution."""
+    import torch
+    maxh = maxw = 8
+    ratios, C, H, W = [1, 2, 4], 10, 360, 640
+    g = dm.Geometry(maxh=maxh, maxw=maxw, ratios=ratios, multiscale=True, hImg=H, wImg=W,
+                    output_extraction_method="max")
+    gen = torch.Generator(device="cuda").manual_seed(9)
+
+    def pyramid(shifts):
+        # shifts[i]: (dy, dx) of scale i in that scale's pixels, or None = unrelated frames
+        inp = []
+        for r, sh in zip(ratios, shifts):
+            h, w = H // r, W // r
+            f2 = torch.randn((C, h + maxh - 1, w + maxw - 1), device="cuda", generator=gen)
+            if sh is None:
+                f1 = torch.randn((C, h, w), device="cuda", generator=gen)
+            else:
+                f1 = f2[:, 3 + sh[0]:3 + sh[0] + h, 3 + sh[1]:3 + sh[1] + w].clone()
+            inp.append((f1, f2))
+        return inp
+
+    out = dm.getModelMultiscale(g, True, True).forward(pyramid([(0, 0)] * 3))
+    torch.cuda.synchronize()
+    assert bool((out["index"] == 28).all())
+    assert bool((out["flow_y"] == 0).all()) and bool((out["flow_x"] == 0).all())
+    # fine scale sees (2,-2), scale 2 the consistent (1,-1), scale 4 nothing: the cascade puts
+    # 2 on the fine entry (2,-2) and at most ~1 anywhere else
+    out = dm.getModelMultiscale(g, True, True).forward(pyramid([(2, -2), (1, -1), None]))
+    torch.cuda.synchronize()
+    assert float((out["flow_y"] == 2).float().mean()) > 0.999
+    assert float((out["flow_x"] == -2).float().mean()) > 0.999
+    # flow (-4, 4) is outside the fine 8x8 window (rows -3..4): it must come out of scale 2's
+    # ring as (-2, 2) x ratio 2
+    out = dm.getModelMultiscale(g, True, True).forward(pyramid([None, (-2, 2), (-1, 1)]))
+    torch.cuda.synchronize()
+    assert float((out["flow_y"] == -4).float().mean()) > 0.99
+    assert float((out["flow_x"] == 4).float().mean()) > 0.99
+    idx = out["index"].cpu().numpy()
+    ry, rx = dm.x2yxMulti(g, idx)
+    np.testing.assert_array_equal(ry, out["flow_y"].cpu().numpy())
+    np.testing.assert_array_equal(rx, out["flow_x"].cpu().numpy())
+
+
+def test_c4_radial_polar_400x400(dm, oracle):
+    """configs[3]: 640x360 frames remapped to 400x400 polar maps around the gopro.cal epipole
+    (+16 circular pad columns for a 17-wide kernel), then the 1-D radial search, hWin = 15.
+    A polar map shifted by 5 rows must give radial flow 5; polar -> cartesian -> polar of a
+    smooth image is close to the identity inside the valid disc."""
+    import torch
+    hImg, wImg, hIn, wIn, wK, hWin, C = 360, 640, 400, 400, 17, 15, 10
+    e2 = (641.4552 * wImg / 1280.0, 344.950836 * wImg / 1280.0)
+    rmax = dm.getRMax(hImg, wImg, e2)
+    yy, xx = np.meshgrid(np.arange(hImg), np.arange(wImg), indexing="ij")
+    img = np.stack([np.sin(xx / 23.0) + np.cos(yy / 17.0), np.cos(xx / 31.0) * np.sin(yy / 13.0),
+                    0.002 * xx + 0.003 * yy]).astype(np.float32)
+    lp, rp = (wK - 1) // 2, math.ceil((wK - 1) / 2)
+    pol = dm.cartesian2polar(img, wdst=wIn, hdst=hIn, xcenter=e2[0], ycenter=e2[1], lpadding=lp,
+                             rpadding=rp, rmax=rmax, alpha=1.0)
+    assert pol.shape == (3, hIn, wIn + 16)
+    np.testing.assert_array_equal(pol[:, :, :lp], pol[:, :, wIn:wIn + lp])   # circular padding
+    back = dm.polar2cartesian(pol[:, :, lp:lp + wIn], wImg, hImg, e2[0], e2[1], rmax)
+    r = np.hypot(xx - e2[0], yy - e2[1])
+    # away from the epipole, the frame border (polar samples beyond it are clamped) and the
+    # theta = 0 seam (image.warp does not wrap the last polar column)
+    inside = (r > 8) & (xx > 8) & (xx < wImg - 9) & (yy > 8) & (yy < hImg - 9)
+    inside &= ~((np.abs(yy - e2[1]) < 6) & (xx > e2[0]))
+    err = np.abs(back - img)[:, inside]
+    assert err.mean() < 0.01 and np.quantile(err, 0.999) < 0.1
+    # matcher on 10-channel polar feature maps: in2 10 x 384 x 400, in1 10 x 370 x 400
+    f2 = torch.randn((C, 384, 400), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    f1 = f2[:, 5:5 + 384 - hWin + 1].clone()
+    flow, mn = dm.nn.SpatialRadialMatching(hWin).argmin_flow([f1, f2])
+    torch.cuda.synchronize()
+    assert flow.shape == (370, 400) and bool((flow == 5).all()) and bool((mn == 0).all())
+    depth, conf = dm.flow2depth(dict(hImg=370, wImg=400), flow.cpu().numpy(), (200.0, 185.0), 0.65)
+    assert conf[185, 200] == 0 and depth.max() <= 1.0 + 1e-6
