@@ -629,6 +629,12 @@ static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, int tile_r
     const long long py = (g.W2 + 3) & ~3LL;  // padded pitch
     void *buf = nullptr;
     DM_CHECK(call.alloc(&buf, (size_t)g.N * g.C * g.H2 * py * sizeof(float)));
+    const cudaMemcpyKind kind = host2 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (s2c == (long long)g.H2 * s2y && s2n == (long long)g.C * s2c) {
+      // planes follow each other row after row: one pitched copy for everything
+      DM_CUDA(cudaMemcpy2DAsync(buf, py * sizeof(float), in->in2, s2y * sizeof(float),
+                                g.W2 * sizeof(float), (size_t)g.N * g.C * g.H2, kind, ctx->stream));
+    } else
     // one pitched copy per (n, c) plane keeps arbitrary strides simple
     for (int n = 0; n < g.N; ++n)
       for (int c = 0; c < g.C; ++c) {
@@ -925,20 +931,16 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
 
 }  // namespace dm
 
-extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, int mode,
-                               float *out) {
-  DM_REQUIRE(ctx && in && out, "dm_match_volume: NULL argument");
+namespace dm {
+// the body of dm_match_volume on an open Call (dm_multiscale_extract runs several of these
+// inside one call so that their outputs can live in the call's arena)
+int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode, float *out) {
+  dm_ctx *ctx = call.ctx;
   const bool exact = (mode & DM_VOLUME_EXACT) != 0;
   mode &= ~DM_VOLUME_EXACT;
   DM_REQUIRE(mode == DM_VOLUME_SSD || mode == DM_VOLUME_NEG_SOFTMAX, "dm_match_volume: bad mode %d",
              mode);
-  DM_CUDA(cudaSetDevice(ctx->device));
-  Call call(ctx);
-  if (in->channels > kMaxC) {
-    int rc = generic_match_volume(call, in, maxh, maxw, mode, exact, out);
-    int rf = call.finish();
-    return rc != DM_OK ? rc : rf;
-  }
+  if (in->channels > kMaxC) return generic_match_volume(call, in, maxh, maxw, mode, exact, out);
   Prepared pr;
   DM_CHECK(prepare(call, in, maxh, maxw, VolumeCfg::kTH, &pr));
   const SweepGeom &g = pr.g;
@@ -977,5 +979,16 @@ extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int max
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(VolumeCfg::kThreads), args, smem, ctx->stream));
   prof_end(ctx);
   count_launch(ctx);
-  return call.finish();
+  return DM_OK;
+}
+}  // namespace dm
+
+extern "C" int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, int mode,
+                               float *out) {
+  DM_REQUIRE(ctx && in && out, "dm_match_volume: NULL argument");
+  DM_CUDA(cudaSetDevice(ctx->device));
+  Call call(ctx);
+  const int rc = match_volume_on(call, in, maxh, maxw, mode, out);
+  const int rf = call.finish();
+  return rc != DM_OK ? rc : rf;
 }

@@ -11,6 +11,8 @@
 
 namespace dm {
 
+int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode, float *out);
+
 constexpr int kMaxRatios = 10;  // N_MAX_RATIOS of x2yxMulti2.c:1
 
 struct Ratios {
@@ -189,61 +191,84 @@ struct ScaleMaps {
   const float *p[kMaxRatios];  // per-scale softmax maps [h/r][w/r][maxh*maxw]
 };
 
-// One warp per full-resolution pixel, lanes over the L entries of the joined vector.
+// Entry l of the joined vector (opticalflow_model_multiscale.lua:293-324) -> its cascade chain
+// (CascadingAddTable.lua:108-135): off[l * n + s] = window offset a*maxw+b to read in scale s's
+// map, or -1 when scale s is not on the chain.  Built on the host once per call.
+static void build_chain_table(const Ratios &R, int maxh, int maxw, int L, std::vector<int> *tab) {
+  const int n = R.n, K = maxh * maxw;
+  tab->assign((size_t)L * n, -1);
+  for (int l = 0; l < L; ++l) {
+    int i = 0, a, b, e = l;
+    if (e < K) {
+      a = e / maxw;
+      b = e - a * maxw;
+    } else {
+      e -= K;
+      i = 1;
+      while (e >= R.len[i]) e -= R.len[i++];
+      const int d = R.d[i], top = d * maxw, side = (maxh - 2 * d) * d;
+      if (e < top) {
+        a = e / maxw;
+        b = e - a * maxw;
+      } else if (e < top + side) {
+        e -= top;
+        a = d + e / d;
+        b = e % d;
+      } else if (e < top + 2 * side) {
+        e -= top + side;
+        a = d + e / d;
+        b = maxw - d + e % d;
+      } else {
+        e -= top + 2 * side;
+        a = maxh - d + e / maxw;
+        b = e % maxw;
+      }
+    }
+    for (int s = i;; ++s) {
+      (*tab)[(size_t)l * n + s] = a * maxw + b;
+      if (s + 1 >= n) break;
+      const int rs = R.r[s], r2 = R.r[s + 1], f = r2 / rs;
+      a = maxh * (r2 - rs) / (2 * r2) + a / f;
+      b = maxw * (r2 - rs) / (2 * r2) + b / f;
+    }
+  }
+}
+
+// One warp per full-resolution pixel, lanes over the L entries of the joined vector.  Scale s
+// reads the nearest-upsampled map, i.e. pixel (Y / r_s, X / r_s); the chain is summed coarse to
+// fine like CascadingAddTable does (out[n] = in[n]; out[i] = in[i] + up(out[i+1])).
 __global__ void __launch_bounds__(256)
-ring_argmax_kernel(ScaleMaps maps, int h, int w, int maxh, int maxw, Ratios R, int L, int middle,
-                   long long *index, long long *flow_y, long long *flow_x) {
+ring_argmax_kernel(ScaleMaps maps, const int *chain, int h, int w, int maxh, int maxw, Ratios R, int L,
+                   int middle, long long *index, long long *flow_y, long long *flow_x) {
   const int lane = threadIdx.x & 31;
-  const int K = maxh * maxw;
+  const int K = maxh * maxw, n = R.n;
   const long long npx = (long long)h * w;
   for (long long px = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); px < npx;
        px += (long long)gridDim.x * 8) {
     const int Y = (int)(px / w), X = (int)(px % w);
+    const float *base[kMaxRatios];
+#pragma unroll
+    for (int s = 0; s < kMaxRatios; ++s)
+      if (s < n) {
+        const int rs = R.r[s];
+        base[s] = maps.p[s] + ((long long)(Y / rs) * (w / rs) + (X / rs)) * K;
+      }
     float best = -__int_as_float(0x7f800000), vmid = 0.0f;
     int lb = 0x7fffffff;
     for (int l = lane; l < L; l += 32) {
-      // entry l of the joined vector -> (scale i, a, b)   (multiscale.lua:293-324)
-      int i = 0, a, b, e = l;
-      if (e < K) {
-        a = e / maxw;
-        b = e - a * maxw;
-      } else {
-        e -= K;
-        i = 1;
-        while (e >= R.len[i]) e -= R.len[i++];
-        const int d = R.d[i], top = d * maxw, side = (maxh - 2 * d) * d;
-        if (e < top) {
-          a = e / maxw;
-          b = e - a * maxw;
-        } else if (e < top + side) {
-          e -= top;
-          a = d + e / d;
-          b = e % d;
-        } else if (e < top + 2 * side) {
-          e -= top + side;
-          a = d + e / d;
-          b = maxw - d + e % d;
-        } else {
-          e -= top + 2 * side;
-          a = maxh - d + e / maxw;
-          b = e % maxw;
+      const int *off = chain + (size_t)l * n;
+      float v = 0.0f;
+      bool first = true;
+#pragma unroll
+      for (int s = kMaxRatios - 1; s >= 0; --s)
+        if (s < n) {
+          const int o = __ldg(off + s);
+          if (o >= 0) {
+            const float x = __ldg(base[s] + o);
+            v = first ? x : __fadd_rn(x, v);
+            first = false;
+          }
         }
-      }
-      // cascade chain, coarse to fine (CascadingAddTable.lua:108-135); scale s reads the
-      // nearest-upsampled map, i.e. pixel (Y / r_s, X / r_s)
-      float vals[kMaxRatios];
-      int depth = 0;
-      for (int s = i;; ++s) {
-        const int rs = R.r[s];
-        const int ws = w / rs;
-        vals[depth++] = __ldg(maps.p[s] + ((long long)(Y / rs) * ws + (X / rs)) * K + a * maxw + b);
-        if (s + 1 >= R.n) break;
-        const int r2 = R.r[s + 1], f = r2 / rs;
-        a = maxh * (r2 - rs) / (2 * r2) + a / f;
-        b = maxw * (r2 - rs) / (2 * r2) + b / f;
-      }
-      float v = vals[depth - 1];
-      for (int j = depth - 2; j >= 0; --j) v = __fadd_rn(vals[j], v);
       if (l + 1 == middle) vmid = v;
       if (v > best) {
         best = v;
@@ -394,13 +419,19 @@ int dm_multiscale_extract(dm_ctx *ctx, const float *const *in1, const float *con
   const int K = maxh * maxw;
   int L = K;
   for (int i = 1; i < nratios; ++i) L += R.len[i];
-  // per-scale soft-max maps live in one allocation that must outlive the per-scale calls,
-  // so it is taken outside the per-call arena
+  // one Call for everything: the per-scale soft-max maps and the chain table live in its arena
   size_t total = 0;
   for (int i = 0; i < nratios; ++i) total += (size_t)(h / ratios[i]) * (w / ratios[i]) * K;
-  float *maps_dev = nullptr;
   DM_CUDA(cudaSetDevice(ctx->device));
-  DM_CUDA(cudaMalloc(&maps_dev, total * sizeof(float)));
+  Call call(ctx);
+  void *mp = nullptr, *tp = nullptr;
+  DM_CHECK(call.alloc(&mp, total * sizeof(float)));
+  float *maps_dev = static_cast<float *>(mp);
+  std::vector<int> table;
+  build_chain_table(R, maxh, maxw, L, &table);
+  DM_CHECK(call.alloc(&tp, table.size() * sizeof(int)));
+  DM_CUDA(cudaMemcpyAsync(tp, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice,
+                          ctx->stream));  // pageable source: staged before the call returns
   ScaleMaps maps;
   memset(&maps, 0, sizeof(maps));
   size_t off = 0;
@@ -417,11 +448,10 @@ int dm_multiscale_extract(dm_ctx *ctx, const float *const *in1, const float *con
     pr.h2 = pr.h1 + maxh - 1;
     pr.w2 = pr.w1 + maxw - 1;
     maps.p[i] = maps_dev + off;
-    rc = dm_match_volume(ctx, &pr, maxh, maxw, DM_VOLUME_NEG_SOFTMAX, maps_dev + off);
+    rc = match_volume_on(call, &pr, maxh, maxw, DM_VOLUME_NEG_SOFTMAX, maps_dev + off);
     off += (size_t)pr.h1 * pr.w1 * K;
   }
   if (rc == DM_OK) {
-    Call call(ctx);
     const long long npx = (long long)h * w;
     void *didx = nullptr, *dfy = nullptr, *dfx = nullptr;
     if (index) rc = call.out(index, (size_t)npx * 8, &didx);
@@ -434,16 +464,13 @@ int dm_multiscale_extract(dm_ctx *ctx, const float *const *in1, const float *con
       const long long cap = (long long)ctx->num_sms * 16;
       if (blocks > cap) blocks = cap;
       ring_argmax_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(
-          maps, h, w, maxh, maxw, R, L, middle, static_cast<long long *>(didx),
-          static_cast<long long *>(dfy), static_cast<long long *>(dfx));
+          maps, static_cast<const int *>(tp), h, w, maxh, maxw, R, L, middle,
+          static_cast<long long *>(didx), static_cast<long long *>(dfy), static_cast<long long *>(dfx));
       count_launch(ctx);
     }
-    const int rf = call.finish();
-    if (rc == DM_OK) rc = rf;
   }
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(maps_dev);
-  return rc;
+  const int rf = call.finish();
+  return rc != DM_OK ? rc : rf;
 }
 
 }  // extern "C"

@@ -1,0 +1,69 @@
+"""Side measurements of the other BASELINE.json configurations (not the bench.py headline):
+kernel-level timings with CUDA events, inputs resident in HBM."""
+import json, math, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "depth-estimation_b200"))
+import torch
+import depthmatch as dm
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    g = torch.Generator(device="cuda").manual_seed(1)
+    res = {}
+    # c1-like: 320x180 -> 2-layer filter output 10x161x301, window 17x17
+    in2 = torch.randn((1, 10, 161, 301), device="cuda", generator=g)
+    in1 = in2[:, :, 8:8 + 145, 8:8 + 285] + 0.05 * torch.randn((1, 10, 145, 285), device="cuda", generator=g)
+    ms = timed(lambda: dm.match_extract(in1, in2, 17, 17, want=("index", "pmax", "score_thr")))
+    res["c1 10x161x301 17x17 (1 pair)"] = {"ms": ms, "pairs_per_s": 1e3 / ms}
+    # c2: 64 pairs of 320x180, 33x33
+    in2 = torch.randn((64, 10, 180, 320), device="cuda", generator=g)
+    in1 = in2[:, :, 16:16 + 148, 16:16 + 288] + 0.05 * torch.randn((64, 10, 148, 288), device="cuda", generator=g)
+    ms = timed(lambda: dm.match_extract(in1, in2, 33, 33, want=("index", "pmax", "score_thr")))
+    res["c2 64 x 320x180 33x33"] = {"ms": ms, "pairs_per_s": 64e3 / ms}
+    # c3: multiscale 640x360, ratios 1,2,4, 8x8
+    geo = dm.Geometry(maxh=8, maxw=8, ratios=[1, 2, 4], multiscale=True, hImg=360, wImg=640, output_extraction_method="max")
+    inp = []
+    for r in (1, 2, 4):
+        h, w = 360 // r, 640 // r
+        f2 = torch.randn((10, h + 7, w + 7), device="cuda", generator=g)
+        inp.append((f2[:, 3:3 + h, 3:3 + w].contiguous(), f2))
+    model = dm.getModelMultiscale(geo, True, True)
+    ms = timed(lambda: model.forward(inp))
+    res["c3 multiscale 640x360 {1,2,4} 8x8"] = {"ms": ms, "pairs_per_s": 1e3 / ms}
+    # c4: polar remap 640x360 -> 400x(400+16), radial matcher hWin 15 on 10x384x400
+    img = torch.rand((3, 360, 640), device="cuda", generator=g)
+    e2 = (320.73, 172.48)
+    rmax = dm.getRMax(360, 640, e2)
+    ms_remap = timed(lambda: dm.cartesian2polar(img, wdst=400, hdst=400, xcenter=e2[0], ycenter=e2[1], lpadding=8, rpadding=8, rmax=rmax))
+    f2 = torch.randn((10, 384, 400), device="cuda", generator=g)
+    f1 = f2[:, 5:5 + 370].contiguous()
+    rm = dm.nn.SpatialRadialMatching(15)
+    ms_match = timed(lambda: rm.argmin_flow([f1, f2]))
+    res["c4 polar remap 3x360x640 -> 400x416"] = {"ms": ms_remap}
+    res["c4 radial match 10x384x400 hWin 15"] = {"ms": ms_match}
+    # c5: 1080p, 65x65, one pair and one of 8 row bands
+    in2 = torch.randn((10, 1080, 1920), device="cuda", generator=g)
+    in1 = in2[:, 32:32 + 1016, 32:32 + 1856] + 0.05 * torch.randn((10, 1016, 1856), device="cuda", generator=g)
+    ms = timed(lambda: dm.match_extract(in1, in2, 65, 65, want=("index", "pmax", "score_thr")), reps=3, warm=1)
+    res["c5 1920x1080 65x65 (1 pair, 1 GPU)"] = {"ms": ms, "pairs_per_s": 1e3 / ms, "alu_frac": 2 * 10 * 4225 * 1016 * 1856 / (ms / 1e3) / (148 * 128 * 1.965e9)}
+    a, b = in1[:, :127], in2[:, :127 + 64]
+    ms = timed(lambda: dm.match_extract(a, b, 65, 65, want=("index", "pmax", "score_thr")), reps=3, warm=1)
+    res["c5 one of 8 row bands (127 rows + 64 halo)"] = {"ms": ms}
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
