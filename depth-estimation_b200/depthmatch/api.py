@@ -21,6 +21,7 @@ __all__ = [
     "x2yxMulti", "x2yxMulti2", "x2yxMultiNumber", "getModelMultiscale", "multiscaleLength",
     "getRMax", "getC2PMask", "getP2CMask", "cartesian2polar", "polar2cartesian", "getKOutput",
     "getP2CMaskOF", "flow2depth", "match_extract", "match_volume", "round_lua",
+    "postProcessImage", "enlargeMask", "radial", "computeDepthMapFromFlow",
 ]
 
 try:  # torch is plumbing only (device memory + streams); the package works without it
@@ -873,3 +874,54 @@ def flow2depth(networkp, flow, center=None, kinfty=0.65, ctx=None):
     check(c._lib.dm_flow2depth(c.handle, fptr, h, w, float(center[0]), float(center[1]), float(infty),
                                dptr, cptr))
     return depth / infty, confs
+
+
+# ------------------------------------------------------------------ next rows
+# opticalflow_model.lua:323-472
+def postProcessImage(inp, mask, winsize, method, ctx=None):
+    args = _Args(ctx)
+    iptr, a = args.inp(inp)
+    mptr, m = args.inp(mask)
+    c = args.ctx_for(a, m)
+    _, h, w = a.shape
+    optr, out = args.out((2, h, w), np.float32, like=a)
+    check(c._lib.dm_post_process_image(c.handle, iptr, mptr, h, w, int(winsize),
+                                       1 if method == "max" else 0, optr))
+    return out
+
+
+# depth_estimation_api.lua:76-132 (in place, returns the mask like the reference)
+def enlargeMask(mask, ix, iy, ctx=None):
+    _check_inplace(mask, np.float32, mask.shape)
+    c = _Args(ctx).ctx_for(mask)
+    h, w = mask.shape
+    check(c._lib.dm_enlarge_mask(c.handle, _ptr(mask), h, w, int(ix), int(iy)))
+    return mask
+
+
+# test_opticalflow.lua:143-216
+def radial(geometry, flow, mh=None, mw=None, ctx=None):
+    args = _Args(ctx)
+    fptr, f = args.inp(flow)
+    c = args.ctx_for(f)
+    _, h, w = f.shape
+    mh = h / 2 if mh is None else mh
+    mw = w / 2 if mw is None else mw
+    rptr, ret = args.out((h, w), np.float32, like=f)
+    cptr, conf = args.out((h, w), np.float32, like=f)
+    check(c._lib.dm_radial_depth(c.handle, fptr, h, w, float(mh), float(mw), float(geometry.wImg / 2),
+                                 rptr, cptr))
+    return ret, conf
+
+
+# ardrone/ardrone_api.cpp:99-140
+def computeDepthMapFromFlow(xflow, mask, imu_translation_x, ctx=None):
+    args = _Args(ctx)
+    xptr, x = args.inp(xflow)
+    mptr, m = args.inp(mask)
+    c = args.ctx_for(x, m)
+    h, w = x.shape
+    dptr, depth = args.out((h, w), np.float32, like=x)
+    cptr, conf = args.out((h, w), np.float32, like=x)
+    check(c._lib.dm_depth_from_xflow(c.handle, xptr, mptr, h, w, float(imu_translation_x), dptr, cptr))
+    return depth, conf

@@ -192,6 +192,22 @@ int dm_p2c_mask(dm_ctx *ctx, int wsrc, int hsrc, int wdst, int hdst, double xcen
 int dm_flow2depth(dm_ctx *ctx, const float *flow, int h, int w, float xcenter, float ycenter,
                   float infty, float *depth, float *confs);
 
+/* ---- next rows: the steps right after the matching path ----------- */
+/* postProcessImage(input, mask, winsize, method) (opticalflow_model.lua:323-472): input/output
+ * [2][h][w] (y-flow, x-flow); method_max = 0: masked k x k median ('med'), 1: mode of the rounded
+ * flow ('max', 16 x 16 histogram semantics).  winsize <= 5 (the reference's scratch size). */
+int dm_post_process_image(dm_ctx *ctx, const float *input, const float *mask, int h, int w,
+                          int winsize, int method_max, float *output);
+/* enlargeMask(mask, ix, iy) (depth_estimation_api.lua:76-132), in place */
+int dm_enlarge_mask(dm_ctx *ctx, float *mask, int h, int w, int ix, int iy);
+/* radial(geometry, flow, mh, mw) (test_opticalflow.lua:143-193): flow [2][h][w] -> depth, conf */
+int dm_radial_depth(dm_ctx *ctx, const float *flow, int h, int w, float mh, float mw, float infty,
+                    float *ret, float *conf);
+/* ARdroneAPI::computeDepthMapFromFlow (ardrone/ardrone_api.cpp:99-140): 6 x 6 masked mode filter
+ * of the rounded x-flow, then depth = m * |x - w/2| / |flow| */
+int dm_depth_from_xflow(dm_ctx *ctx, const float *xflow, const float *mask, int h, int w, float m,
+                        float *depth, float *conf);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -164,6 +164,24 @@ void orc_warp_bilinear(const float *src, int C, int hs, int ws, const float *fie
 void orc_flow2depth(const float *flow, int h, int w, float xcenter, float ycenter,
                     float infty, float *depth, float *confs);
 
+/* ---- postprocess.c ("next" rows: the steps right after the matching path) ---- */
+
+/* postProcessImage(input, mask, winsize, method) (opticalflow_model.lua:323-472): input/output
+ * [2][h][w] (y-flow, x-flow), masked k x k median ('med') or mode ('max') filter.
+ * PINNED against the reference's inline C (oracle/_ref). */
+void orc_post_process_image(const float *input, const float *mask, int h, int w, int k, int method_max,
+                            float *output);
+void orc_pp_median(const float *flow, const float *mask, int h, int w, int k, float *ret);
+void orc_pp_mode(const float *flow, const float *mask, int h, int w, int k, float *ret);
+/* enlargeMask (depth_estimation_api.lua:76-132), in place.  PINNED against oracle/_ref. */
+void orc_enlarge_mask(float *mask, int h, int w, int ix, int iy);
+/* radial() (test_opticalflow.lua:143-193).  PINNED against oracle/_ref. */
+void orc_radial_depth(const float *flow, int h, int w, float mh, float mw, float infty, float *ret,
+                      float *conf);
+/* ARdroneAPI::computeDepthMapFromFlow (ardrone/ardrone_api.cpp:99-140).  PARITY UNPINNED. */
+void orc_depth_from_xflow(const float *xflow, const float *mask, int h, int w, float m, float *depth,
+                          float *conf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,7 @@ typedef struct luaL_reg {
 const void *luaT_checktypename2id(lua_State *L, const char *tname);
 void *luaT_checkudata(lua_State *L, int idx, const void *id);
 double lua_tonumber(lua_State *L, int idx);
+long lua_tointeger(lua_State *L, int idx);
 int luaL_getn(lua_State *L, int idx);
 void lua_pushnumber(lua_State *L, double v);
 void lua_gettable(lua_State *L, int idx);

@@ -40,6 +40,8 @@ double lua_tonumber(lua_State *L, int idx) {
   return s->kind == SHIM_NUMBER ? s->number : 0.0; /* nil -> 0 like Lua */
 }
 
+long lua_tointeger(lua_State *L, int idx) { return (long)lua_tonumber(L, idx); }
+
 int luaL_getn(lua_State *L, int idx) { return at(L, idx)->table_n; }
 
 void lua_pushnumber(lua_State *L, double v) { shim_push_number(L, v); }

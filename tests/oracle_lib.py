@@ -301,3 +301,91 @@ def flow2depth(flow, xc, yc, infty):
     lib().orc_flow2depth(pf, h, w, C.c_float(xc), C.c_float(yc), C.c_float(infty),
                          depth.ctypes.data_as(c_fp), confs.ctypes.data_as(c_fp))
     return depth, confs
+
+
+# ------------------------------------------------------------- postprocess
+def post_process_image(inp, mask, k, method, which="oracle"):
+    """postProcessImage(input [2,h,w], mask [h,w], winsize, 'med'|'max')."""
+    inp, pi = _f(inp)
+    mask, pm = _f(mask)
+    _, h, w = inp.shape
+    out = np.zeros((2, h, w), np.float32)
+    if which == "oracle":
+        lib().orc_post_process_image(pi, pm, h, w, k, 1 if method == "max" else 0,
+                                     out.ctypes.data_as(c_fp))
+        return out
+    r = ref()
+    assert r is not None, "oracle/_ref not built"
+    if method == "max":  # the Lua around the inline C (opticalflow_model.lua:435-439)
+        rr = np.floor(inp + np.float32(0.5)).astype(np.float32)
+        m = rr.min()
+        rr = np.ascontiguousarray(rr - m)
+        r.ref_pp_filter(1, rr.ctypes.data_as(c_fp), pm, k, C.c_long(h), C.c_long(w), out.ctypes.data_as(c_fp))
+        return out + m
+    r.ref_pp_filter(0, pi, pm, k, C.c_long(h), C.c_long(w), out.ctypes.data_as(c_fp))
+    return out
+
+
+def enlarge_mask(mask, ix, iy, which="oracle"):
+    m = np.ascontiguousarray(mask, np.float32).copy()
+    h, w = m.shape
+    if which == "oracle":
+        lib().orc_enlarge_mask(m.ctypes.data_as(c_fp), h, w, ix, iy)
+    else:
+        ref().ref_enlarge_mask(m.ctypes.data_as(c_fp), C.c_long(h), C.c_long(w), ix, iy)
+    return m
+
+
+def radial_depth(flow, mh, mw, infty, which="oracle"):
+    flow, pf = _f(flow)
+    _, h, w = flow.shape
+    ret = np.zeros((h, w), np.float32)
+    conf = np.zeros((h, w), np.float32)
+    if which == "oracle":
+        lib().orc_radial_depth(pf, h, w, C.c_float(mh), C.c_float(mw), C.c_float(infty),
+                               ret.ctypes.data_as(c_fp), conf.ctypes.data_as(c_fp))
+    else:
+        ref().ref_radial_depth(pf, C.c_long(h), C.c_long(w), C.c_double(mh), C.c_double(mw),
+                               ret.ctypes.data_as(c_fp), conf.ctypes.data_as(c_fp), C.c_double(infty))
+    return ret, conf
+
+
+def depth_from_xflow(xflow, mask, m):
+    xflow, px = _f(xflow)
+    mask, pm = _f(mask)
+    h, w = xflow.shape
+    depth = np.empty((h, w), np.float32)
+    conf = np.empty((h, w), np.float32)
+    lib().orc_depth_from_xflow(px, pm, h, w, C.c_float(m), depth.ctypes.data_as(c_fp),
+                               conf.ctypes.data_as(c_fp))
+    return depth, conf
+
+
+def ref_c2p_mask(wdst, hdst, xc, yc, rmax, alpha=1.0):
+    """getC2PMask's inline C through oracle/_ref (un-padded), with the Lua-side constants."""
+    import math
+    m = np.empty((2, hdst, wdst), np.float32)
+    ref().ref_c2p_mask(m.ctypes.data_as(c_fp), C.c_long(hdst), C.c_long(wdst), C.c_double(xc),
+                       C.c_double(yc), C.c_double(rmax / (hdst ** alpha)),
+                       C.c_double(2 * math.pi / wdst), C.c_double(alpha))
+    return m
+
+
+def ref_p2c_mask(wsrc, hsrc, wdst, hdst, xc, yc, rmax, alpha=1.0):
+    import math
+    m = np.empty((2, hdst, wdst), np.float32)
+    pi2 = 2 * math.pi
+    ref().ref_p2c_mask(m.ctypes.data_as(c_fp), C.c_long(hdst), C.c_long(wdst), C.c_double(xc),
+                       C.c_double(yc), C.c_double(wsrc / pi2), C.c_double(hsrc / (rmax ** (1.0 / alpha))),
+                       C.c_double(pi2), C.c_double(1.0 / alpha))
+    return m
+
+
+def ref_flow2depth(flow, xc, yc, infty):
+    flow, pf = _f(flow)
+    h, w = flow.shape
+    depth = np.zeros((h, w), np.float32)   # `ret` starts at zero, `confs` at one (display.lua:12-13)
+    confs = np.ones((h, w), np.float32)
+    ref().ref_flow2depth(pf, C.c_long(h), C.c_long(w), depth.ctypes.data_as(c_fp),
+                         confs.ctypes.data_as(c_fp), C.c_double(xc), C.c_double(yc), C.c_double(infty))
+    return depth, confs

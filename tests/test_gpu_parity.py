@@ -551,3 +551,45 @@ def test_c4_radial_polar_400x400(dm, oracle):
     assert flow.shape == (370, 400) and bool((flow == 5).all()) and bool((mn == 0).all())
     depth, conf = dm.flow2depth(dict(hImg=370, wImg=400), flow.cpu().numpy(), (200.0, 185.0), 0.65)
     assert conf[185, 200] == 0 and depth.max() <= 1.0 + 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows: the steps right after the matching path, bit-exact with the oracle
+# (which is itself pinned against the reference's inline C, tests/test_oracle_ref.py)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["med", "max"])
+@pytest.mark.parametrize("k", [3, 5])
+def test_post_process_image_vs_oracle(dm, oracle, method, k):
+    rng = np.random.default_rng(k + 7)
+    flow = np.clip(np.rint(rng.normal(0, 3, (2, 90, 160))), -7, 8).astype(np.float32)
+    if method == "med":
+        flow = flow + rng.random((2, 90, 160)).astype(np.float32)
+    else:
+        flow = flow + (rng.random((2, 90, 160)).astype(np.float32) - 0.5) * 0.8
+    mask = (rng.random((90, 160)) > 0.3).astype(np.float32)
+    mask[20:30, 40:60] = 0
+    want = oracle.post_process_image(flow, mask, k, method)
+    np.testing.assert_array_equal(dm.postProcessImage(flow, mask, k, method), want)
+
+
+def test_enlarge_mask_radial_and_drone_depth_vs_oracle(dm, oracle):
+    rng = np.random.default_rng(21)
+    for ix, iy in ((16, 16), (3, 5), (1, 1)):
+        mask = (rng.random((180, 320)) > 0.35).astype(np.float32)
+        mask[7] = 0
+        mask[:, 11] = 0
+        want = oracle.enlarge_mask(mask, ix, iy)
+        got = dm.enlargeMask(mask.copy(), ix, iy)
+        np.testing.assert_array_equal(got, want)
+    flow = (rng.normal(0, 2, (2, 180, 320)) * (rng.random((2, 180, 320)) > 0.2)).astype(np.float32)
+    g = dm.Geometry(wImg=320, hImg=180)
+    wr, wc = oracle.radial_depth(flow, 125.8, 155.2, 160.0)
+    gr, gc = dm.radial(g, flow, 125.8, 155.2)
+    np.testing.assert_array_equal(gr, wr)
+    np.testing.assert_array_equal(gc, wc)
+    xflow = np.clip(rng.normal(0, 3, (180, 320)), -8, 11).astype(np.float32)
+    mask = (rng.random((180, 320)) > 0.2).astype(np.float32)
+    wd, wcf = oracle.depth_from_xflow(xflow, mask, 0.37)
+    gd, gcf = dm.computeDepthMapFromFlow(xflow, mask, 0.37)
+    np.testing.assert_array_equal(gd, wd)
+    np.testing.assert_array_equal(gcf, wcf)

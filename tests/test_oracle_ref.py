@@ -60,3 +60,57 @@ def test_reference_c_decode_diverges_from_lua_spec(oracle):
     rc, sy, sx = oracle.x2yx_multi_number(8, 8, [1, 2], 64)
     assert rc == 0 and (sy, sx) == (4, 4)
     assert (int(ry[0, 0]), int(rx[0, 0])) != (sy, sx)
+
+
+# ---- the reference's `inline.load` C bodies, extracted verbatim (oracle/extract_inline.py) ----
+@pytest.mark.parametrize("method", ["med", "max"])
+@pytest.mark.parametrize("k", [3, 5])
+def test_post_process_image_matches_reference_inline_c(oracle, method, k):
+    _need_ref(oracle)
+    rng = np.random.default_rng(k)
+    # the mode filter indexes a 16 x 16 histogram without a range check: flows span < 16 values
+    flow = np.clip(np.rint(rng.normal(0, 3, (2, 31, 44))), -7, 8).astype(np.float32)
+    if method == "med":
+        flow = flow + rng.random((2, 31, 44)).astype(np.float32)
+    mask = (rng.random((31, 44)) > 0.3).astype(np.float32)
+    mask[10:14, 20:26] = 0  # windows without a single masked pixel
+    a = oracle.post_process_image(flow, mask, k, method, "oracle")
+    b = oracle.post_process_image(flow, mask, k, method, "ref")
+    np.testing.assert_array_equal(a, b)
+
+
+def test_enlarge_mask_matches_reference_inline_c(oracle):
+    _need_ref(oracle)
+    rng = np.random.default_rng(1)
+    for ix, iy in ((3, 2), (1, 1), (7, 9), (0, 4)):
+        mask = (rng.random((25, 33)) > 0.4).astype(np.float32)
+        mask[5] = 0
+        mask[:, 7] = 0
+        np.testing.assert_array_equal(oracle.enlarge_mask(mask, ix, iy, "oracle"),
+                                      oracle.enlarge_mask(mask, ix, iy, "ref"))
+
+
+def test_radial_depth_matches_reference_inline_c(oracle):
+    _need_ref(oracle)
+    rng = np.random.default_rng(2)
+    flow = (rng.normal(0, 2, (2, 40, 60)) * (rng.random((2, 40, 60)) > 0.2)).astype(np.float32)
+    a = oracle.radial_depth(flow, 19.5, 31.25, 30.0, "oracle")
+    b = oracle.radial_depth(flow, 19.5, 31.25, 30.0, "ref")
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_polar_luts_and_flow2depth_match_reference_inline_c(oracle):
+    _need_ref(oracle)
+    for (wd, hd, xc, yc, rmax, alpha) in ((48, 50, 40.09, 21.56, 45.0, 1.0), (400, 400, 320.73, 172.48, 367.0, 1.0),
+                                          (64, 32, 30.5, 17.25, 33.0, 1.5)):
+        np.testing.assert_array_equal(oracle.c2p_mask(wd, hd, xc, yc, 0, 0, rmax, alpha),
+                                      oracle.ref_c2p_mask(wd, hd, xc, yc, rmax, alpha))
+        np.testing.assert_array_equal(oracle.p2c_mask(wd, hd, 80, 45, xc, yc, rmax, alpha),
+                                      oracle.ref_p2c_mask(wd, hd, 80, 45, xc, yc, rmax, alpha))
+    rng = np.random.default_rng(3)
+    flow = (rng.random((37, 41)) * 2).astype(np.float32)
+    a = oracle.flow2depth(flow, 20.3, 18.9, 55.5)
+    b = oracle.ref_flow2depth(flow, 20.3, 18.9, 55.5)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
