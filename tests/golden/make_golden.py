@@ -5,7 +5,8 @@ mounted and oracle/_ref is built from the reference's own sources):
 
 Two kinds of vectors:
   * ref_*.npz    -- inputs + outputs of the REFERENCE's own native code (oracle/_ref:
-                    version2/extract_output.cpp, x2yxMulti2.c compiled as-is).  These pin the
+                    version2/extract_output.cpp, x2yxMulti2.c and the inline.load C bodies of
+                    the Lua files, compiled as-is).  These pin the
                     oracle (tests/test_golden.py, CPU) and the CUDA kernels (GPU).
   * oracle_*.npz -- inputs + outputs of the oracle restatement for the parts whose arithmetic
                     lives in un-vendored Torch7 code (matching, softmax, cascade, polar remap):
@@ -24,8 +25,46 @@ import oracle_lib as O  # noqa: E402
 from synth import make_pair  # noqa: E402
 
 
+def inline_vectors():
+    """ref_inline.npz: the reference's inline.load C bodies (oracle/extract_inline.py compiles them
+    verbatim into oracle/_ref): postProcessImage fmed/fmax, enlargeMask, radial(), polar LUTs,
+    flow2depth."""
+    rng = np.random.default_rng(20261019)
+    h, w = 36, 64
+    base = np.clip(np.rint(rng.normal(0, 3, (2, h, w))), -7, 8).astype(np.float32)
+    flow_med = base + rng.random((2, h, w)).astype(np.float32)
+    flow_max = base + (rng.random((2, h, w)).astype(np.float32) - 0.5) * 0.8
+    mask = (rng.random((h, w)) > 0.3).astype(np.float32)
+    mask[10:16, 20:30] = 0
+    out = {"flow_med": flow_med, "flow_max": flow_max, "mask": mask}
+    for k in (3, 5):
+        out["med%d" % k] = O.post_process_image(flow_med, mask, k, "med", "ref")
+        out["max%d" % k] = O.post_process_image(flow_max, mask, k, "max", "ref")
+    emask = (rng.random((h, w)) > 0.35).astype(np.float32)
+    emask[5] = 0
+    emask[:, 9] = 0
+    out["emask"] = emask
+    out["emask_4_3"] = O.enlarge_mask(emask, 4, 3, "ref")
+    out["emask_16_16"] = O.enlarge_mask(emask, 16, 16, "ref")
+    rflow = (rng.normal(0, 2, (2, h, w)) * (rng.random((2, h, w)) > 0.2)).astype(np.float32)
+    rd, rc = O.radial_depth(rflow, 25.3, 31.7, w / 2, "ref")
+    out.update(rflow=rflow, rcentre=np.array([25.3, 31.7, w / 2]), rdepth=rd, rconf=rc)
+    e2 = (641.4552 * 80 / 1280.0, 344.950836 * 80 / 1280.0)
+    rmax = O.get_rmax(45, 80, *e2)
+    out.update(polar_geom=np.array([45, 80, 50, 48]), polar_e2=np.array(e2), polar_rmax=np.float64(rmax),
+               c2p=O.ref_c2p_mask(48, 50, e2[0], e2[1], rmax), p2c=O.ref_p2c_mask(48, 50, 80, 45, e2[0], e2[1], rmax))
+    pflow = (rng.random((50, 48)) * 9 * (rng.random((50, 48)) > 0.1)).astype(np.float32)
+    fd, fc = O.ref_flow2depth(pflow, e2[0], e2[1], 1000.0)
+    out.update(pflow=pflow, fdepth=fd, fconf=fc)
+    np.savez_compressed(os.path.join(HERE, "ref_inline.npz"), **out)
+
+
 def main():
     assert O.ref() is not None, "build oracle/_ref first (make -C oracle)"
+    if "--inline-only" in sys.argv:
+        inline_vectors()
+        return
+    inline_vectors()
     rng = np.random.default_rng(20261018)
 
     # ---- reference native code: extractOutput / extractOutputMarginalized

@@ -50,6 +50,47 @@ def test_oracle_regression_vectors(oracle):
     np.testing.assert_array_equal(oracle.warp_bilinear(z["img"], m), z["polar"])
 
 
+def test_oracle_matches_reference_inline_c_vectors(oracle):
+    z = load("ref_inline.npz")
+    for k in (3, 5):
+        np.testing.assert_array_equal(oracle.post_process_image(z["flow_med"], z["mask"], k, "med"), z["med%d" % k])
+        np.testing.assert_array_equal(oracle.post_process_image(z["flow_max"], z["mask"], k, "max"), z["max%d" % k])
+    np.testing.assert_array_equal(oracle.enlarge_mask(z["emask"], 4, 3), z["emask_4_3"])
+    np.testing.assert_array_equal(oracle.enlarge_mask(z["emask"], 16, 16), z["emask_16_16"])
+    mh, mw, infty = [float(v) for v in z["rcentre"]]
+    rd, rc = oracle.radial_depth(z["rflow"], mh, mw, infty)
+    np.testing.assert_array_equal(rd, z["rdepth"])
+    np.testing.assert_array_equal(rc, z["rconf"])
+    hImg, wImg, hIn, wIn = [int(v) for v in z["polar_geom"]]
+    e2, rmax = z["polar_e2"], float(z["polar_rmax"])
+    np.testing.assert_array_equal(oracle.c2p_mask(wIn, hIn, e2[0], e2[1], 0, 0, rmax, 1.0), z["c2p"])
+    np.testing.assert_array_equal(oracle.p2c_mask(wIn, hIn, wImg, hImg, e2[0], e2[1], rmax, 1.0), z["p2c"])
+    fd, fc = oracle.flow2depth(z["pflow"], e2[0], e2[1], 1000.0)
+    np.testing.assert_array_equal(fd, z["fdepth"])
+    np.testing.assert_array_equal(fc, z["fconf"])
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_inline_c_vectors(dm):
+    z = load("ref_inline.npz")
+    for k in (3, 5):
+        np.testing.assert_array_equal(dm.postProcessImage(z["flow_med"], z["mask"], k, "med"), z["med%d" % k])
+        np.testing.assert_array_equal(dm.postProcessImage(z["flow_max"], z["mask"], k, "max"), z["max%d" % k])
+    np.testing.assert_array_equal(dm.enlargeMask(z["emask"].copy(), 4, 3), z["emask_4_3"])
+    np.testing.assert_array_equal(dm.enlargeMask(z["emask"].copy(), 16, 16), z["emask_16_16"])
+    mh, mw, infty = [float(v) for v in z["rcentre"]]
+    rd, rc = dm.radial(dm.Geometry(wImg=int(2 * infty), hImg=36), z["rflow"], mh, mw)
+    np.testing.assert_array_equal(rd, z["rdepth"])
+    np.testing.assert_array_equal(rc, z["rconf"])
+    hImg, wImg, hIn, wIn = [int(v) for v in z["polar_geom"]]
+    e2, rmax = z["polar_e2"], float(z["polar_rmax"])
+    # the LUTs hold sin/cos/pow results: the device's libm differs from glibc in the last ulp
+    np.testing.assert_allclose(dm.getC2PMask(wImg, hImg, wIn, hIn, e2[0], e2[1], 0, 0, rmax), z["c2p"],
+                               rtol=0, atol=2e-4)
+    np.testing.assert_allclose(dm.getP2CMask(wIn, hIn, wImg, hImg, e2[0], e2[1], rmax), z["p2c"], rtol=0,
+                               atol=2e-4)
+
+
 @pytest.mark.gpu
 def test_cuda_extract_output_matches_reference_vectors(dm):
     z = load("ref_extract_output.npz")
