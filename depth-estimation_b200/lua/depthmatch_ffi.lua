@@ -53,6 +53,13 @@ int dm_warp_bilinear(dm_ctx *ctx, const float *src, int c, int hs, int ws, const
                      int hd, int wd, float *dst);
 int dm_flow2depth(dm_ctx *ctx, const float *flow, int h, int w, float xcenter, float ycenter,
                   float infty, float *depth, float *confs);
+int dm_post_process_image(dm_ctx *ctx, const float *input, const float *mask, int h, int w,
+                          int winsize, int method_max, float *output);
+int dm_enlarge_mask(dm_ctx *ctx, float *mask, int h, int w, int ix, int iy);
+int dm_radial_depth(dm_ctx *ctx, const float *flow, int h, int w, float mh, float mw, float infty,
+                    float *ret, float *conf);
+int dm_depth_from_xflow(dm_ctx *ctx, const float *xflow, const float *mask, int h, int w, float m,
+                        float *depth, float *conf);
 ]]
 
 local M = {}

@@ -143,3 +143,30 @@ function x2yxMulti2(geometry, x, bug_compat)
                             #geometry.ratios, bug_compat and 1 or 0, torch.data(rety), torch.data(retx)))
    return rety, retx
 end
+
+-- ---------------------------------------------------------------- post-processing (no inline.load)
+-- opticalflow_model.lua:323-472
+function postProcessImage(input, mask, winsize, method)
+   local inp, m = input:contiguous(), mask:contiguous()
+   local output = torch.Tensor(2, inp:size(2), inp:size(3))
+   dm.check(C.dm_post_process_image(ctx, torch.data(inp), torch.data(m), inp:size(2), inp:size(3), winsize,
+                                    method == 'max' and 1 or 0, torch.data(output)))
+   return output
+end
+
+-- depth_estimation_api.lua:76-132 (in place)
+function enlargeMask(mask, ix, iy)
+   assert(mask:isContiguous())
+   dm.check(C.dm_enlarge_mask(ctx, torch.data(mask), mask:size(1), mask:size(2), ix, iy))
+   return mask
+end
+
+-- test_opticalflow.lua:143-216
+function radial(geometry, flow, mh, mw)
+   local f = flow:contiguous()
+   local h, w = f:size(2), f:size(3)
+   local ret, conf = torch.Tensor(h, w), torch.Tensor(h, w)
+   dm.check(C.dm_radial_depth(ctx, torch.data(f), h, w, mh or h / 2, mw or w / 2, geometry.wImg / 2,
+                              torch.data(ret), torch.data(conf)))
+   return ret, conf
+end
