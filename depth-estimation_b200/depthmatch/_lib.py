@@ -36,6 +36,12 @@ class dm_extract_out(C.Structure):
                 ("soft_yx", C.c_void_p), ("n_untouched", C.c_void_p)]
 
 
+class dm_conv_layer(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("n_out", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+                ("n_conn", C.c_int32), ("tanh_after", C.c_int32),
+                ("conn", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/depthmatch.h declaration by declaration
 _P, _I, _D, _L, _F = C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_float
 SIGNATURES = {
@@ -78,6 +84,10 @@ SIGNATURES = {
     "dm_enlarge_mask": (_I, [_P, _P, _I, _I, _I, _I]),
     "dm_radial_depth": (_I, [_P, _P, _I, _I, _F, _F, _F, _P, _P]),
     "dm_depth_from_xflow": (_I, [_P, _P, _P, _I, _I, _F, _P, _P]),
+    "dm_filter_create": (_I, [_P, C.POINTER(dm_conv_layer), _I, C.POINTER(_P)]),
+    "dm_filter_destroy": (_I, [_P]),
+    "dm_filter_output_size": (_I, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "dm_filter_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -22,6 +22,7 @@ __all__ = [
     "getRMax", "getC2PMask", "getP2CMask", "cartesian2polar", "polar2cartesian", "getKOutput",
     "getP2CMaskOF", "flow2depth", "match_extract", "match_volume", "round_lua",
     "postProcessImage", "enlargeMask", "radial", "computeDepthMapFromFlow",
+    "Filter", "getFilter", "getRadialFilter", "getMultiscalePrefilter", "downsample",
 ]
 
 try:  # torch is plumbing only (device memory + streams); the package works without it
@@ -408,11 +409,253 @@ class OutputExtractor(_Module):
         return self.output
 
 
+# ------------------------------------------------------------------ feature extractor
+class _Tables:
+    """nn.tables (Torch7 nn): connection tables, rows of 1-based (from, to)."""
+
+    @staticmethod
+    def full(nin, nout):
+        return np.array([[i + 1, o + 1] for o in range(nout) for i in range(nin)], np.int32)
+
+    @staticmethod
+    def random(nin, nout, nto, rng=None):
+        """nn.tables.random(nin, nout, nto): every output plane reads `nto` distinct input planes,
+        drawn as consecutive chunks of a random permutation (re-drawn when used up).  The
+        permutation comes from numpy's generator, not Torch7's Mersenne stream."""
+        rng = rng if rng is not None else np.random.default_rng()
+        tbl = np.zeros((nout * nto, 2), np.int32)
+        nfi = nin // nto
+        if nfi < 1:
+            raise DepthMatchError(_lib.DM_ERR_INVALID, "nn.tables.random: nto > nin")
+        fi, cnt = rng.permutation(nin), 0
+        for o in range(nout):
+            tbl[o * nto:(o + 1) * nto, 0] = fi[cnt * nto:(cnt + 1) * nto] + 1
+            tbl[o * nto:(o + 1) * nto, 1] = o + 1
+            cnt += 1
+            if cnt == nfi:
+                fi, cnt = rng.permutation(nin), 0
+        return tbl
+
+
+class SpatialConvolution(_Module):
+    """nn.SpatialConvolution(nInputPlane, nOutputPlane, kW, kH): valid cross-correlation,
+    weight [nOut, nIn, kH, kW], bias [nOut]; reset() = uniform(+-1/sqrt(kW*kH*nIn))."""
+
+    def __init__(self, nInputPlane, nOutputPlane, kW, kH, rng=None):
+        self.nInputPlane, self.nOutputPlane, self.kW, self.kH = nInputPlane, nOutputPlane, kW, kH
+        self.connTable = None
+        self.reset(rng)
+
+    def reset(self, rng=None):
+        rng = rng if rng is not None else np.random.default_rng()
+        stdv = 1.0 / math.sqrt(self.kW * self.kH * self.nInputPlane)
+        self.weight = rng.uniform(-stdv, stdv, (self.nOutputPlane, self.nInputPlane, self.kH, self.kW)).astype(np.float32)
+        self.bias = rng.uniform(-stdv, stdv, self.nOutputPlane).astype(np.float32)
+
+    def updateOutput(self, inp):
+        return Filter([self]).forward(inp)
+
+
+class SpatialConvolutionMap(_Module):
+    """nn.SpatialConvolutionMap(connTable, kW, kH): weight [nConn, kH, kW], bias [nOut]."""
+
+    def __init__(self, connTable, kW, kH, rng=None):
+        self.connTable = np.ascontiguousarray(connTable, np.int32)
+        self.kW, self.kH = kW, kH
+        self.nInputPlane = int(self.connTable[:, 0].max())
+        self.nOutputPlane = int(self.connTable[:, 1].max())
+        self.reset(rng)
+
+    def reset(self, rng=None):
+        rng = rng if rng is not None else np.random.default_rng()
+        n = self.connTable.shape[0]
+        self.weight = np.empty((n, self.kH, self.kW), np.float32)
+        self.bias = np.empty(self.nOutputPlane, np.float32)
+        for o in range(self.nOutputPlane):
+            rows = np.nonzero(self.connTable[:, 1] == o + 1)[0]
+            stdv = 1.0 / math.sqrt(self.kW * self.kH * max(len(rows), 1))
+            self.weight[rows] = rng.uniform(-stdv, stdv, (len(rows), self.kH, self.kW))
+            self.bias[o] = rng.uniform(-stdv, stdv)
+
+    def updateOutput(self, inp):
+        return Filter([self]).forward(inp)
+
+
+class Tanh(_Module):
+    def updateOutput(self, inp):
+        raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED, "nn.Tanh runs fused behind a convolution (Filter)")
+
+
+class Filter(_Module):
+    """The nn.Sequential getFilter returns (opticalflow_model.lua:45-79): convolution layers with
+    nn.Tanh between them.  forward(input): [C,H,W] or a batch [N,C,H,W] (numpy or torch CUDA);
+    pads = (l, r, t, b) is an nn.SpatialZeroPadding in front (multiscale prefilter).  The weights
+    are packed on the device at the first forward; call reset_weights() after editing them."""
+
+    def __init__(self, modules, ctx=None):
+        self.modules, self.ctx = list(modules), ctx
+        self._handle, self._handle_ctx = None, None
+        self.output = None
+
+    def add(self, m):
+        self.modules.append(m)
+        self.reset_weights()
+        return self
+
+    def getWeights(self):
+        convs = [m for m in self.modules if hasattr(m, "weight")]
+        return {"layer%d" % (i + 1): m.weight for i, m in enumerate(convs)}
+
+    def reset_weights(self):
+        if self._handle is not None:
+            self._handle_ctx._lib.dm_filter_destroy(self._handle)
+        self._handle, self._handle_ctx = None, None
+
+    __del__ = reset_weights
+
+    def _layers(self):
+        out = []
+        for m in self.modules:
+            if isinstance(m, Tanh):
+                if not out:
+                    raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED, "a Filter starts with a convolution")
+                out[-1][1] = 1
+            else:
+                out.append([m, 0])
+        return out
+
+    def _build(self, c):
+        if self._handle is not None and self._handle_ctx is c:
+            return self._handle
+        self.reset_weights()
+        layers = self._layers()
+        arr = (_lib.dm_conv_layer * len(layers))()
+        keep = []
+        for i, (m, tanh) in enumerate(layers):
+            w = np.ascontiguousarray(m.weight, np.float32)
+            b = np.ascontiguousarray(m.bias, np.float32)
+            keep += [w, b]
+            arr[i].n_in, arr[i].n_out, arr[i].kh, arr[i].kw = m.nInputPlane, m.nOutputPlane, m.kH, m.kW
+            arr[i].tanh_after = tanh
+            arr[i].weight, arr[i].bias = w.ctypes.data, b.ctypes.data
+            if m.connTable is not None:
+                t = np.ascontiguousarray(m.connTable, np.int32)
+                keep.append(t)
+                arr[i].n_conn, arr[i].conn = t.shape[0], t.ctypes.data
+                if w.shape != (t.shape[0], m.kH, m.kW):
+                    raise DepthMatchError(_lib.DM_ERR_INVALID, "SpatialConvolutionMap: weight shape")
+            elif w.shape != (m.nOutputPlane, m.nInputPlane, m.kH, m.kW):
+                raise DepthMatchError(_lib.DM_ERR_INVALID, "SpatialConvolution: weight shape")
+        h = C.c_void_p()
+        check(c._lib.dm_filter_create(c.handle, arr, len(layers), C.byref(h)))
+        self._handle, self._handle_ctx = h, c
+        return h
+
+    def output_size(self, h, w, pads=(0, 0, 0, 0)):
+        for m in self.modules:
+            if hasattr(m, "weight"):
+                h, w = h - m.kH + 1, w - m.kW + 1
+        return h + pads[2] + pads[3], w + pads[0] + pads[1]
+
+    def updateOutput(self, inp, pads=(0, 0, 0, 0)):
+        args = _Args(self.ctx)
+        iptr, a = args.inp(inp)
+        c = args.ctx_for(a)
+        single = len(a.shape) == 3
+        shp = (1,) + tuple(a.shape) if single else tuple(a.shape)
+        n, cin, h, w = shp
+        fh = self._build(c)
+        co, ho, wo = C.c_int(), C.c_int(), C.c_int()
+        check(c._lib.dm_filter_output_size(fh, h, w, *[int(v) for v in pads], C.byref(co), C.byref(ho),
+                                           C.byref(wo)))
+        convs = [m for m in self.modules if hasattr(m, "weight")]
+        if cin != convs[0].nInputPlane:
+            raise DepthMatchError(_lib.DM_ERR_INVALID, "Filter: %d input planes, the first layer takes %d"
+                                  % (cin, convs[0].nInputPlane))
+        optr, out = args.out((n, co.value, ho.value, wo.value), np.float32, like=a)
+        check(c._lib.dm_filter_forward(c.handle, fh, iptr, n, h, w, *[int(v) for v in pads], optr))
+        self.output = out[0] if single else out
+        return self.output
+
+    def forward(self, inp, pads=(0, 0, 0, 0)):
+        return self.updateOutput(inp, pads)
+
+    __call__ = forward
+
+
+# opticalflow_model.lua:45-79 (layers[i] = {nIn, kW, kH, nOut}, tanh between layers)
+def getFilter(geometry, rng=None, ctx=None):
+    if geometry.L2Pooling:
+        raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED, "getFilter: L2Pooling (the reference asserts too)")
+    rng = rng if rng is not None else np.random.default_rng()
+    mods, layers = [], geometry.layers
+    for i, l in enumerate(layers):
+        if i == 0 or layers[i - 1][3] == l[0]:
+            mods.append(SpatialConvolution(l[0], l[3], l[1], l[2], rng))
+        else:
+            mods.append(SpatialConvolutionMap(_Tables.random(layers[i - 1][3], l[3], l[0], rng), l[1], l[2], rng))
+        if i != len(layers) - 1:
+            mods.append(Tanh())
+    return Filter(mods, ctx=ctx)
+
+
+# radial/radial_opticalflow_network.lua:6-31 (layers: 'tanh' or {nIn, kH, kW, nOut})
+def getRadialFilter(networkp, rng=None, ctx=None):
+    rng = rng if rng is not None else np.random.default_rng()
+    mods, last = [], None
+    for l in networkp["layers"]:
+        if isinstance(l, str):
+            if l != "tanh":
+                raise DepthMatchError(_lib.DM_ERR_INVALID, "Unknown layer %r" % (l,))
+            mods.append(Tanh())
+        elif last is None or l[0] == last:
+            mods.append(SpatialConvolution(l[0], l[3], l[2], l[1], rng))
+            last = l[3]
+        else:
+            mods.append(SpatialConvolutionMap(_Tables.random(last, l[3], l[0], rng), l[2], l[1], rng))
+            last = l[3]
+    return Filter(mods, ctx=ctx)
+
+
+# opticalflow_model_multiscale.lua:134-173
+def getMultiscalePrefilter(geometry, filter, ctx=None):
+    """Returns prefilter(img [C,H,W]) -> one feature map per ratio: r x r average
+    (nn.SpatialDownSampling), zero padding of the patch footprint, the (shared) filter."""
+    wPad, hPad = geometry.wPatch2 - 1, geometry.hPatch2 - 1
+    pads = (wPad // 2, wPad - wPad // 2, hPad // 2, hPad - hPad // 2)
+    filters = [filter if (geometry.share_filters or i == 0) else Filter(filter.modules, ctx=ctx)
+               for i in range(len(geometry.ratios))]
+
+    def prefilter(img):
+        outs = []
+        for r, f in zip(geometry.ratios, filters):
+            outs.append(f.forward(downsample(img, r, ctx=ctx) if r != 1 else img, pads))
+        return outs
+
+    prefilter.getWeights = filter.getWeights
+    return prefilter
+
+
+def downsample(img, r, ctx=None):
+    """nn.SpatialDownSampling(r, r): r x r average (opticalflow_model_multiscale.lua:145)."""
+    args = _Args(ctx)
+    iptr, a = args.inp(img)
+    c = args.ctx_for(a)
+    ch, h, w = a.shape
+    optr, out = args.out((ch, h // r, w // r), np.float32, like=a)
+    check(c._lib.dm_downsample_avg(c.handle, iptr, ch, h, w, r, optr))
+    return out
+
+
 class _NN:
     SpatialMatching = SpatialMatching
     SpatialRadialMatching = SpatialRadialMatching
     CascadingAddTable = CascadingAddTable
     OutputExtractor = OutputExtractor
+    SpatialConvolution = SpatialConvolution
+    SpatialConvolutionMap = SpatialConvolutionMap
+    Tanh = Tanh
+    tables = _Tables
 
 
 nn = _NN()
@@ -508,13 +751,39 @@ class DenseMatch(_Module):
         return self.output
 
 
-def getModel(geometry, full_image=True, prefiltered=True, fused=False, ctx=None):
-    if not prefiltered:
-        raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED, "getModel: the conv feature extractor "
-                              "(getFilter) is outside the matching hot path; pass prefiltered maps")
+class _FilteredModel(_Module):
+    """getModel(geometry, full_image, prefiltered=false) (opticalflow_model.lua:81-92): the
+    shared-weight filter on both patches (nn.ParallelTable of a filter and its clone), then the
+    matcher.  forward({patch1, patch2}) as prepareInput returns them."""
+
+    def __init__(self, geometry, matcher, filter, ctx=None):
+        self.geometry, self.matcher, self.filter, self.ctx = geometry, matcher, filter, ctx
+        self.modules = [[filter, filter], matcher]
+        self.output = None
+
+    def getWeights(self):
+        return self.filter.getWeights()
+
+    def updateOutput(self, inp):
+        p1, p2 = inp
+        if tuple(p1.shape) == tuple(p2.shape):  # one launch per layer for both frames
+            both = torch.stack([p1, p2]) if _is_torch(p1) else np.stack([p1, p2])
+            f = self.filter.forward(both)
+            f1, f2 = f[0], f[1]
+        else:
+            c = (lambda x: x.contiguous()) if _is_torch(p1) else np.ascontiguousarray
+            f1, f2 = self.filter.forward(c(p1)), self.filter.forward(c(p2))
+        self.output = self.matcher.forward([f1, f2])
+        return self.output
+
+
+def getModel(geometry, full_image=True, prefiltered=False, fused=False, filter=None, rng=None, ctx=None):
     if geometry.multiscale:
         return getModelMultiscale(geometry, full_image, prefiltered, ctx=ctx)
-    return DenseMatch(geometry, ctx=ctx) if fused else _MatchModel(geometry, ctx=ctx)
+    matcher = DenseMatch(geometry, ctx=ctx) if fused else _MatchModel(geometry, ctx=ctx)
+    if prefiltered:
+        return matcher
+    return _FilteredModel(geometry, matcher, filter or getFilter(geometry, rng, ctx), ctx=ctx)
 
 
 # opticalflow_model.lua:153-169

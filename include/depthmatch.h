@@ -208,6 +208,33 @@ int dm_radial_depth(dm_ctx *ctx, const float *flow, int h, int w, float mh, floa
 int dm_depth_from_xflow(dm_ctx *ctx, const float *xflow, const float *mask, int h, int w, float m,
                         float *depth, float *conf);
 
+/* ---- next row 3: the feature extractor in front of the path ---------------------- */
+/* One layer of getFilter (opticalflow_model.lua:45-79; radial/radial_opticalflow_network.lua:6-31).
+ * n_conn == 0: nn.SpatialConvolution(n_in, n_out, kw, kh), weight [n_out][n_in][kh][kw].
+ * n_conn  > 0: nn.SpatialConvolutionMap(conn, kw, kh), conn = n_conn rows of 1-based (from, to)
+ *              as nn.tables.random builds them, weight [n_conn][kh][kw].
+ * bias [n_out]; tanh_after = an nn.Tanh follows.  weight, bias and conn are HOST pointers, read
+ * at dm_filter_create only. */
+typedef struct dm_conv_layer {
+  int32_t n_in, n_out, kh, kw;
+  int32_t n_conn;
+  int32_t tanh_after;
+  const int32_t *conn;
+  const float *weight;
+  const float *bias;
+} dm_conv_layer;
+typedef struct dm_filter dm_filter;
+/* getFilter(geometry): the weights are packed and kept on the context's device */
+int dm_filter_create(dm_ctx *ctx, const dm_conv_layer *layers, int n_layers, dm_filter **out);
+int dm_filter_destroy(dm_filter *filter);
+int dm_filter_output_size(const dm_filter *filter, int h, int w, int pad_l, int pad_r, int pad_t,
+                          int pad_b, int *channels, int *hout, int *wout);
+/* filter:forward on n_img images [n_img][n_in][h][w] (both frames of a pair share the weights,
+ * opticalflow_model.lua:85-90), zero-padded first like nn.SpatialZeroPadding(l, r, t, b)
+ * (opticalflow_model_multiscale.lua:136-146) -> [n_img][n_out][hout][wout] */
+int dm_filter_forward(dm_ctx *ctx, const dm_filter *filter, const float *in, int n_img, int h, int w,
+                      int pad_l, int pad_r, int pad_t, int pad_b, float *out);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

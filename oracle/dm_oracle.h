@@ -182,6 +182,17 @@ void orc_radial_depth(const float *flow, int h, int w, float mh, float mw, float
 void orc_depth_from_xflow(const float *xflow, const float *mask, int h, int w, float m, float *depth,
                           float *conf);
 
+/* ---- filter.c ("next" row 3: the feature extractor in front of the path) ---- */
+
+/* One layer of getFilter (opticalflow_model.lua:45-79): nn.SpatialConvolution (conn == NULL,
+ * weight [n_out][n_in][kh][kw]) or nn.SpatialConvolutionMap (conn = n_conn 1-based (from,to)
+ * rows as nn.tables.random makes them, weight [n_conn][kh][kw]), valid cross-correlation on the
+ * zero-padded input (nn.SpatialZeroPadding, multiscale.lua:146), optional nn.Tanh.
+ * out: n_out x (h+pad_t+pad_b-kh+1) x (w+pad_l+pad_r-kw+1).  PARITY UNPINNED (Torch7 nn). */
+void orc_conv_layer(const float *in, int n_in, int h, int w, const float *weight, const float *bias,
+                    int n_out, int kh, int kw, const int32_t *conn, int n_conn, int pad_l, int pad_r,
+                    int pad_t, int pad_b, int tanh_after, float *out, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

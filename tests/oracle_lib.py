@@ -389,3 +389,37 @@ def ref_flow2depth(flow, xc, yc, infty):
     ref().ref_flow2depth(pf, C.c_long(h), C.c_long(w), depth.ctypes.data_as(c_fp),
                          confs.ctypes.data_as(c_fp), C.c_double(xc), C.c_double(yc), C.c_double(infty))
     return depth, confs
+
+
+# ------------------------------------------------------------- filter (feature extractor)
+def conv_layer(inp, weight, bias, conn=None, pads=(0, 0, 0, 0), tanh=False, nthreads=0):
+    """One getFilter layer.  inp [n_in,h,w]; weight [n_out,n_in,kh,kw] (conn None) or
+    [n_conn,kh,kw] with conn [n_conn,2] 1-based (from,to); pads = (l, r, t, b)."""
+    inp, pi = _f(inp)
+    weight, pw = _f(weight)
+    bias, pb = _f(bias)
+    n_in, h, w = inp.shape
+    n_out = bias.shape[0]
+    kh, kw = weight.shape[-2:]
+    if conn is None:
+        assert weight.shape[:2] == (n_out, n_in)
+        pc, nc = None, 0
+    else:
+        conn = np.ascontiguousarray(conn, np.int32)
+        assert conn.shape == (weight.shape[0], 2)
+        pc, nc = conn.ctypes.data_as(C.c_void_p), conn.shape[0]
+    pl, pr, pt, pbm = pads
+    ho, wo = h + pt + pbm - kh + 1, w + pl + pr - kw + 1
+    out = np.empty((n_out, ho, wo), np.float32)
+    lib().orc_conv_layer(pi, n_in, h, w, pw, pb, n_out, kh, kw, pc, nc, pl, pr, pt, pbm, int(bool(tanh)),
+                         out.ctypes.data_as(c_fp), int(nthreads))
+    return out
+
+
+def filter_forward(inp, layers, pads=(0, 0, 0, 0)):
+    """layers: list of dicts(weight, bias, conn=None, tanh=False); padding before the first."""
+    x = inp
+    for i, L in enumerate(layers):
+        x = conv_layer(x, L["weight"], L["bias"], L.get("conn"), pads if i == 0 else (0, 0, 0, 0),
+                       L.get("tanh", False))
+    return x

@@ -593,3 +593,97 @@ def test_enlarge_mask_radial_and_drone_depth_vs_oracle(dm, oracle):
     gd, gcf = dm.computeDepthMapFromFlow(xflow, mask, 0.37)
     np.testing.assert_array_equal(gd, wd)
     np.testing.assert_array_equal(gcf, wcf)
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" row 3: the feature extractor (getFilter / getMultiscalePrefilter), fp32 within 1e-4
+# ---------------------------------------------------------------------------------------------
+def _oracle_layers(flt, dm):
+    layers = []
+    for m in flt.modules:
+        if isinstance(m, dm.nn.Tanh):
+            layers[-1]["tanh"] = True
+        else:
+            layers.append(dict(weight=m.weight, bias=m.bias, conn=m.connTable))
+    return layers
+
+
+def _assert_close_fp32(got, want, rel=1e-4):
+    scale = float(np.abs(want).max())
+    np.testing.assert_allclose(got, want, rtol=rel, atol=rel * scale)
+
+
+def test_filter_c1_geometry_vs_oracle(dm, oracle):
+    """c1's filter {3,5,5,8} tanh {4,16,16,10}: a full convolution, then a
+    SpatialConvolutionMap with nn.tables.random(8, 10, 4)."""
+    rng = np.random.default_rng(1)
+    g = dm.Geometry(layers=[[3, 5, 5, 8], [4, 16, 16, 10]])
+    flt = dm.getFilter(g, rng)
+    assert flt.modules[2].connTable.shape == (40, 2) and isinstance(flt.modules[1], dm.nn.Tanh)
+    for o in range(10):   # every output plane reads 4 distinct input planes
+        rows = flt.modules[2].connTable[flt.modules[2].connTable[:, 1] == o + 1, 0]
+        assert len(rows) == 4 and len(set(rows)) == 4
+    img = rng.random((3, 90, 160)).astype(np.float32)
+    want = oracle.filter_forward(img, _oracle_layers(flt, dm))
+    got = flt.forward(img)
+    assert got.shape == want.shape == (10, 71, 141)
+    _assert_close_fp32(got, want)
+    # batch of both frames = two single calls, bit for bit; device tensors too
+    img2 = rng.random((3, 90, 160)).astype(np.float32)
+    both = flt.forward(np.stack([img, img2]))
+    np.testing.assert_array_equal(both[0], got)
+    np.testing.assert_array_equal(both[1], flt.forward(img2))
+    import torch
+    dev = flt.forward(torch.from_numpy(np.stack([img, img2])).cuda())
+    assert dev.is_cuda
+    np.testing.assert_array_equal(dev.cpu().numpy(), both)
+
+
+@pytest.mark.parametrize("shape,layers", [
+    ((3, 40, 70), [[3, 1, 17, 5], [5, 17, 1, 10]]),               # radial net: 1x17 then 17x1
+    ((3, 40, 70), [[3, 3, 3, 4], "tanh", [4, 7, 2, 6], "tanh"]),  # ragged kernels, trailing tanh
+    ((1, 33, 65), [[1, 1, 1, 2]]),                                  # 1x1
+    ((10, 50, 60), [[10, 17, 17, 10]]),                             # widest footprint used anywhere
+])
+def test_radial_filter_shapes_vs_oracle(dm, oracle, shape, layers):
+    rng = np.random.default_rng(2)
+    flt = dm.getRadialFilter(dict(layers=layers), rng)
+    img = rng.standard_normal(shape).astype(np.float32)
+    want = oracle.filter_forward(img, _oracle_layers(flt, dm))
+    _assert_close_fp32(flt.forward(img), want)
+
+
+def test_multiscale_prefilter_and_raw_frames_end_to_end(dm, oracle):
+    """c3 from raw frames: downsample -> zero padding -> shared {3,5,5,10} filter per scale,
+    and getModel(prefiltered=false): filter on both patches, then the fused matcher."""
+    rng = np.random.default_rng(3)
+    g = dm.Geometry(layers=[[3, 5, 5, 10]], ratios=[1, 2, 4], multiscale=True, share_filters=True,
+                    wPatch2=5, hPatch2=5, maxh=8, maxw=8)
+    flt = dm.getFilter(g, rng)
+    pre = dm.getMultiscalePrefilter(g, flt)
+    img = rng.random((3, 64, 96)).astype(np.float32)
+    feats = pre(img)
+    layers = _oracle_layers(flt, dm)
+    for r, f in zip(g.ratios, feats):
+        small = oracle.downsample_avg(img, r) if r != 1 else img
+        want = oracle.filter_forward(small, layers, pads=(2, 2, 2, 2))
+        assert f.shape == (10, 64 // r, 96 // r)
+        _assert_close_fp32(f, want)
+    # single scale, raw frames in, flow out
+    g1 = dm.Geometry(layers=[[3, 5, 5, 8], [4, 16, 16, 10]], maxh=9, maxw=9, hImg=80, wImg=120)
+    flt1 = dm.getFilter(g1, rng)
+    base = rng.random((3, 90, 130)).astype(np.float32)
+    fr2 = base[:, 5:85, 5:125]
+    fr1 = base[:, 3:83, 7:127]          # frame 1 pixel (y,x) = frame 2 pixel (y-2, x+2)
+    model = dm.getModel(g1, True, False, fused=True, filter=flt1)
+    out = model.forward(dm.prepareInput(g1, fr1, fr2))
+    f1 = oracle.filter_forward(np.ascontiguousarray(dm.prepareInput(g1, fr1, fr2)[0]), _oracle_layers(flt1, dm))
+    f2 = oracle.filter_forward(fr2, _oracle_layers(flt1, dm))
+    prob = oracle.neg_softmax(oracle.spatial_matching(f1, f2, 9, 9))
+    idx, _ = oracle.argmax_tie(prob, 81, dm.getMiddleIndex(g1))
+    gap = oracle.top2_relgap(prob, 81)
+    got = np.asarray(out["index"]).reshape(-1)
+    bad = (got != idx) & (gap >= 1e-3)   # features differ by ~1e-6 relative: allow near-ties
+    assert bad.sum() == 0
+    dy, dx = dm.x2yx(g1, got.reshape(f1.shape[1:]))
+    assert np.median(dy) - 5 == -2 and np.median(dx) - 5 == 2

@@ -164,3 +164,60 @@ def test_flow2depth_rules(oracle):
     assert conf[20, 25] == 0 and depth[20, 25] == 0          # within 10 px of the epipole
     assert depth[5, 5] == 99.0                               # flow < 0.1 -> infinity
     np.testing.assert_allclose(depth[0, 0], math.hypot(25, 20) / 2.0, rtol=1e-6)
+
+
+# ---- T7/T8: the feature extractor (getFilter) ------------------------------------------------
+def _dense_from_map(conn, wm, n_in, n_out):
+    wd = np.zeros((n_out, n_in) + wm.shape[1:], np.float32)
+    for e, (f, t) in enumerate(conn):
+        wd[t - 1, f - 1] += wm[e]
+    return wd
+
+
+def test_conv_layer_equals_an_independent_conv2d(oracle):
+    """T7: nn.SpatialConvolution / SpatialConvolutionMap + SpatialZeroPadding + Tanh against
+    torch's conv2d (an independent implementation of the same valid cross-correlation)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((3, 23, 31)).astype(np.float32)
+    w = rng.standard_normal((8, 3, 5, 5)).astype(np.float32) * 0.2
+    b = rng.standard_normal(8).astype(np.float32)
+    got = oracle.conv_layer(x, w, b, pads=(1, 2, 3, 0), tanh=True)
+    want = torch.tanh(F.conv2d(F.pad(torch.from_numpy(x)[None], (1, 2, 3, 0)), torch.from_numpy(w),
+                               torch.from_numpy(b)))[0].numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+    conn = np.array([[f + 1, t + 1] for t in range(10) for f in rng.permutation(8)[:4]], np.int32)
+    wm = rng.standard_normal((40, 16, 16)).astype(np.float32) * 0.05
+    bm = rng.standard_normal(10).astype(np.float32)
+    x8 = rng.standard_normal((8, 30, 41)).astype(np.float32)
+    got = oracle.conv_layer(x8, wm, bm, conn)
+    want = F.conv2d(torch.from_numpy(x8)[None], torch.from_numpy(_dense_from_map(conn, wm, 8, 10)),
+                    torch.from_numpy(bm))[0].numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+
+
+def test_patch_unfolding_filter_makes_matching_a_patch_ssd(oracle):
+    """T8 (tests/test_multiscale.lua:44-55,135-166): with identity 'patch-unfolding' weights
+    (output plane (c,i,j) copies input pixel (c, y+i, x+j)), SpatialMatching on the features is
+    the brute-force SSD between k x k patches."""
+    rng = np.random.default_rng(12)
+    k, c = 3, 2
+    w = np.zeros((c * k * k, c, k, k), np.float32)
+    for ci in range(c):
+        for i in range(k):
+            for j in range(k):
+                w[(ci * k + i) * k + j, ci, i, j] = 1
+    b = np.zeros(c * k * k, np.float32)
+    img2 = rng.standard_normal((c, 16, 18)).astype(np.float32)
+    img1 = (np.roll(img2, (-1, -2), (1, 2)) + 0.01 * rng.standard_normal(img2.shape)).astype(np.float32)
+    f1 = oracle.conv_layer(img1[:, 1:-1, 1:-1], w, b)      # 12 x 14
+    f2 = oracle.conv_layer(img2, w, b)                      # 14 x 16
+    vol = oracle.spatial_matching(f1, f2, 3, 3)
+    h1, w1 = f1.shape[1:]
+    for (y, x) in ((0, 0), (5, 7), (h1 - 1, w1 - 1)):
+        p1 = img1[:, 1 + y:1 + y + k, 1 + x:1 + x + k]
+        for dy in range(3):
+            for dx in range(3):
+                p2 = img2[:, y + dy:y + dy + k, x + dx:x + dx + k]
+                np.testing.assert_allclose(vol[y, x, dy, dx], ((p1 - p2) ** 2).sum(), rtol=1e-5, atol=1e-6)
