@@ -11,14 +11,20 @@
 // one output plane of a 32 x 16 sub-tile, a thread a 4 x 4 block of it: per input row and
 // 4-tap chunk it reads 8 floats (two conflict-free LDS.128) and feeds 64 FMAs; the 4-tap weight
 // vectors are warp-uniform (one broadcast LDG.128 each, L1-resident).
+#include <algorithm>
 #include <vector>
 
 #include "dm_common.cuh"
 
 struct dm_filter {
   struct Layer {
-    int n_in, n_out, kh, kw, kw4, n_conn, tanh_after;
-    float *weight;  // [n_conn][kh][kw4], connections grouped by output plane, rows zero padded
+    int n_in, n_out, kh, kw, n_conn, tanh_after;
+    int taps;     // taps per chunk: 5 when kw == 5 (one chunk, no padding), else 4
+    int nchunks;  // chunks per kernel row
+    int rowlen;   // float2 pairs per packed weight row (16-byte multiple)
+    int max_conn_per_out;
+    float *weight;  // [n_conn][kh + 1][rowlen][2]: pairs {w[ky][kx], w[ky-1][kx]}, zero outside;
+                    // connections grouped by output plane
     float *bias;    // [n_out]
     int *row_ptr;   // [n_out + 1]
     int *from;      // [n_conn]
@@ -31,86 +37,129 @@ struct dm_filter {
 namespace dm {
 
 constexpr int kSubW = 32, kSubH = 16;  // warp sub-tile: 8 x 4 lanes of 4 x 4 outputs
+constexpr int kMaxConvWarps = 20;
 
 struct ConvArgs {
   const float *in;
   float *out;
   const float *weight, *bias;
   const int *row_ptr, *from;
-  int n_in, n_out, kh, kw4, tanh_after;
+  int n_in, n_out, kh, nchunks, rowlen, tanh_after;
   int h, w, hout, wout, pad_t, pad_l;
   int tw, th, pitch, rows;
+  int group;       // output planes per weight phase
+  int tile_floats; // offset of the weight stage in shared memory
 };
 
+// One input row of one 4-tap (5-tap) chunk: 8 window floats against the packed weight rows
+// r (output rows 0,1) and r-2 (output rows 2,3).
+template <int J, bool A, bool B>
+__device__ __forceinline__ void conv_step(const float *row, const float2 *wa, const float2 *wb,
+                                          float2 (&acc01)[4], float2 (&acc23)[4]) {
+  const float4 lo = *reinterpret_cast<const float4 *>(row);
+  const float4 hi = *reinterpret_cast<const float4 *>(row + 4);
+  const float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  if (A) {
+    float2 w[6];
+    *reinterpret_cast<float4 *>(&w[0]) = *reinterpret_cast<const float4 *>(wa);
+    *reinterpret_cast<float4 *>(&w[2]) = *reinterpret_cast<const float4 *>(wa + 2);
+    if (J == 5) w[4] = wa[4];
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc01[p] = __ffma2_rn(w[j], make_float2(win[p + j], win[p + j]), acc01[p]);
+  }
+  if (B) {
+    float2 w[6];
+    *reinterpret_cast<float4 *>(&w[0]) = *reinterpret_cast<const float4 *>(wb);
+    *reinterpret_cast<float4 *>(&w[2]) = *reinterpret_cast<const float4 *>(wb + 2);
+    if (J == 5) w[4] = wb[4];
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc23[p] = __ffma2_rn(w[j], make_float2(win[p + j], win[p + j]), acc23[p]);
+  }
+}
+
+template <int J>
 __global__ void conv_tile_kernel(const ConvArgs a) {
-  extern __shared__ __align__(16) float tile[];  // [n_in][rows][pitch]
+  extern __shared__ __align__(16) float tile[];  // [n_in][rows][pitch] | weight stage
+  float2 *wsm = reinterpret_cast<float2 *>(tile + a.tile_floats);
   const int img = blockIdx.z;
   const int ox0 = blockIdx.x * a.tw, oy0 = blockIdx.y * a.th;
   const int plane_s = a.rows * a.pitch;
-  {
-    const float *src = a.in + (size_t)img * a.n_in * a.h * a.w;
-    const int total = a.n_in * plane_s;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int c = idx / plane_s, rem = idx - c * plane_s;
-      const int r = rem / a.pitch, x = rem - r * a.pitch;
-      const int iy = oy0 - a.pad_t + r, ix = ox0 - a.pad_l + x;
-      float v = 0.0f;
-      if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) v = __ldg(src + ((size_t)c * a.h + iy) * a.w + ix);
-      tile[idx] = v;
-    }
-  }
-  __syncthreads();
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int lx = lane & 7, ly = lane >> 3;
-  const int subs_x = a.tw / kSubW, subs = subs_x * (a.th / kSubH);
-  const int n_items = a.n_out * subs;
-  const int wstride = a.kh * a.kw4;
-  for (int item = warp; item < n_items; item += nwarps) {
-    const int to = item / subs, sub = item - to * subs;
-    const int x0 = (sub % subs_x) * kSubW + lx * 4, y0 = (sub / subs_x) * kSubH + ly * 4;
-    float acc[4][4];
-    const float b = __ldg(a.bias + to);
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-#pragma unroll
-      for (int p = 0; p < 4; ++p) acc[t][p] = b;
-    const int e1 = __ldg(a.row_ptr + to + 1);
-    for (int e = __ldg(a.row_ptr + to); e < e1; ++e) {
-      const float *wp = a.weight + (size_t)e * wstride;
-      const float *tp = tile + __ldg(a.from + e) * plane_s + y0 * a.pitch + x0;
-      for (int r = 0; r < a.kh + 3; ++r) {
-        const float *row = tp + r * a.pitch;
-        for (int kx0 = 0; kx0 < a.kw4; kx0 += 4) {
-          const float4 lo = *reinterpret_cast<const float4 *>(row + kx0);
-          const float4 hi = *reinterpret_cast<const float4 *>(row + kx0 + 4);
-          const float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int ky = r - t;  // input row r feeds output row t through tap row r - t
-            if ((unsigned)ky < (unsigned)a.kh) {
-              const float4 wv = __ldg(reinterpret_cast<const float4 *>(wp + ky * a.kw4 + kx0));
-#pragma unroll
-              for (int p = 0; p < 4; ++p) {
-                acc[t][p] = fmaf(win[p], wv.x, acc[t][p]);
-                acc[t][p] = fmaf(win[p + 1], wv.y, acc[t][p]);
-                acc[t][p] = fmaf(win[p + 2], wv.z, acc[t][p]);
-                acc[t][p] = fmaf(win[p + 3], wv.w, acc[t][p]);
-              }
-            }
-          }
-        }
+  {  // input footprint of every plane, zero padding materialised; one warp per row
+    const float *src = a.in + (size_t)img * a.n_in * a.h * a.w;
+    const int nrows = a.n_in * a.rows;
+    for (int row = warp; row < nrows; row += nwarps) {
+      const int c = row / a.rows, r = row - c * a.rows;
+      const int iy = oy0 - a.pad_t + r;
+      const bool row_ok = iy >= 0 && iy < a.h;
+      const float *s = src + ((size_t)c * a.h + (row_ok ? iy : 0)) * a.w;
+      float *d = tile + row * a.pitch;
+      for (int x = lane; x < a.pitch; x += 32) {
+        const int ix = ox0 - a.pad_l + x;
+        d[x] = (row_ok && ix >= 0 && ix < a.w) ? __ldg(s + ix) : 0.0f;
       }
     }
-    float *dst = a.out + ((size_t)img * a.n_out + to) * a.hout * a.wout;
+  }
+
+  const int lx = lane & 7, ly = lane >> 3;
+  const int subs_x = a.tw / kSubW, subs = subs_x * (a.th / kSubH);
+  const int wrow = a.rowlen;                // float2 per packed weight row
+  const int wconn = (a.kh + 1) * wrow;      // float2 per connection
+  for (int g0 = 0; g0 < a.n_out; g0 += a.group) {
+    const int g1 = min(g0 + a.group, a.n_out);
+    const int c0 = __ldg(a.row_ptr + g0), c1 = __ldg(a.row_ptr + g1);
+    __syncthreads();  // the previous phase is done with the weight stage
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(a.weight) + (size_t)c0 * (wconn / 2);
+      float4 *dst = reinterpret_cast<float4 *>(wsm);
+      const int n4 = (c1 - c0) * (wconn / 2);
+      for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int n_items = (g1 - g0) * subs;
+    for (int item = warp; item < n_items; item += nwarps) {
+      const int to = g0 + item / subs, sub = item % subs;
+      const int x0 = (sub % subs_x) * kSubW + lx * 4, y0 = (sub / subs_x) * kSubH + ly * 4;
+      // acc01[p] = output rows (0, 1) of column p, acc23[p] = rows (2, 3): one FFMA2 each
+      float2 acc01[4], acc23[4];
+      const float b = __ldg(a.bias + to);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int oy = oy0 + y0 + t;
-      if (oy >= a.hout) break;
+      for (int p = 0; p < 4; ++p) acc01[p] = acc23[p] = make_float2(b, b);
+      const int e1 = __ldg(a.row_ptr + to + 1);
+      for (int e = __ldg(a.row_ptr + to); e < e1; ++e) {
+        const float2 *wbase = wsm + (e - c0) * wconn;
+        const float *tp = tile + __ldg(a.from + e) * plane_s + y0 * a.pitch + x0;
+        for (int c = 0; c < a.nchunks; ++c) {
+          // input row r feeds output row t through tap row r - t; the packed weight row r
+          // holds {w[r][j], w[r-1][j]}: rows (0,1) use row r, rows (2,3) row r - 2
+          const float *row = tp + c * 4;
+          const float2 *wq = wbase + c * J;
+          conv_step<J, true, false>(row, wq, wq, acc01, acc23);
+          conv_step<J, true, false>(row + a.pitch, wq + wrow, wq, acc01, acc23);
+          row += 2 * a.pitch;
+#pragma unroll 2
+          for (int r = 2; r <= a.kh; ++r, row += a.pitch, wq += wrow)
+            conv_step<J, true, true>(row, wq + 2 * wrow, wq, acc01, acc23);
+          conv_step<J, false, true>(row, wq, wq, acc01, acc23);
+          conv_step<J, false, true>(row + a.pitch, wq, wq + wrow, acc01, acc23);
+        }
+      }
+      float *dst = a.out + ((size_t)img * a.n_out + to) * a.hout * a.wout;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int ox = ox0 + x0 + p;
-        if (ox < a.wout) dst[(size_t)oy * a.wout + ox] = a.tanh_after ? tanhf(acc[t][p]) : acc[t][p];
+      for (int t = 0; t < 4; ++t) {
+        const int oy = oy0 + y0 + t;
+        if (oy >= a.hout) break;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int ox = ox0 + x0 + p;
+          const float2 pr = t < 2 ? acc01[p] : acc23[p];
+          const float v = (t & 1) ? pr.y : pr.x;
+          if (ox < a.wout) dst[(size_t)oy * a.wout + ox] = a.tanh_after ? tanhf(v) : v;
+        }
       }
     }
   }
@@ -128,7 +177,8 @@ static int launch_layer(dm_ctx *ctx, const dm_filter::Layer &L, const float *in,
   a.n_in = L.n_in;
   a.n_out = L.n_out;
   a.kh = L.kh;
-  a.kw4 = L.kw4;
+  a.nchunks = L.nchunks;
+  a.rowlen = L.rowlen;
   a.tanh_after = L.tanh_after;
   a.h = h;
   a.w = w;
@@ -136,34 +186,69 @@ static int launch_layer(dm_ctx *ctx, const dm_filter::Layer &L, const float *in,
   a.wout = w + pad_l + pad_r - L.kw + 1;
   a.pad_t = pad_t;
   a.pad_l = pad_l;
-  // the largest tile whose input footprint fits; prefer two CTAs per SM and a grid that fills
-  // the machine
-  const int cand[4][2] = {{64, 32}, {64, 16}, {32, 16}, {32, 16}};
-  size_t smem = 0;
-  int pick = -1;
-  for (int i = 0; i < 3; ++i) {
-    const int tw = cand[i][0], th = cand[i][1];
-    const size_t bytes = (size_t)L.n_in * (th + L.kh - 1) * (tw + L.kw4) * 4;
-    const long long ctas = (long long)((a.wout + tw - 1) / tw) * ((a.hout + th - 1) / th) * n_img;
-    const bool last = i == 2;
-    if (bytes > ctx->smem_optin) continue;
-    if (!last && (bytes > 110 * 1024 || ctas < 2LL * ctx->num_sms)) continue;
-    pick = i;
-    smem = bytes;
-    break;
+  const void *kernel = L.taps == 5 ? (const void *)conv_tile_kernel<5> : (const void *)conv_tile_kernel<4>;
+  // Tile shape and output planes per weight phase: the combination that wastes the least of
+  // the machine (partial last wave, outputs past the edge, idle warps in a round, too few
+  // resident warps), among those whose input footprint + weight stage fit in shared memory.
+  const int cand[4][2] = {{64, 32}, {64, 16}, {32, 32}, {32, 16}};
+  const size_t out_bytes = (size_t)L.max_conn_per_out * (L.kh + 1) * L.rowlen * 8;  // weights of one plane
+  double best = -1.0;
+  int pick_tw = 0, pick_th = 0, pick_warps = 0, pick_group = 0;
+  size_t pick_smem = 0, pick_tile = 0;
+  for (int i = 0; i < 4; ++i) {
+    for (int per_sm_target = 2; per_sm_target >= 1; --per_sm_target) {
+      const int tw = cand[i][0], th = cand[i][1];
+      const size_t tile_bytes = (size_t)L.n_in * (th + L.kh - 1) * (tw + 4 * L.nchunks) * 4;
+      const size_t budget = per_sm_target == 1 ? ctx->smem_optin : (ctx->smem_optin + 1024) / 2 - 1024;
+      if (tile_bytes + out_bytes > budget) continue;
+      const int group = (int)std::min<size_t>(L.n_out, (budget - tile_bytes) / out_bytes);
+      const size_t bytes = tile_bytes + group * out_bytes;
+      const int subs = (tw / kSubW) * (th / kSubH);
+      const int items = group * subs;
+      const int rounds = (items + kMaxConvWarps - 1) / kMaxConvWarps;
+      const int nwarps = (items + rounds - 1) / rounds;
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        continue;
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nwarps * 32, bytes) != cudaSuccess ||
+          per_sm < 1)
+        continue;
+      const long long ctas = (long long)((a.wout + tw - 1) / tw) * ((a.hout + th - 1) / th) * n_img;
+      const long long slots = (long long)per_sm * ctx->num_sms;
+      const long long waves = (ctas + slots - 1) / slots;
+      const double fill = (double)ctas / (double)(waves * slots);                      // last wave
+      const double edge = (double)a.wout * a.hout * n_img / ((double)ctas * tw * th);  // past the edge
+      int total_rounds = 0;
+      for (int g0 = 0; g0 < L.n_out; g0 += group)
+        total_rounds += (std::min(group, L.n_out - g0) * subs + nwarps - 1) / nwarps;
+      const double lanes = (double)L.n_out * subs / ((double)total_rounds * nwarps);   // idle warps
+      const double resident = std::min(1.0, per_sm * nwarps / 16.0);                   // latency hiding
+      const double score = fill * edge * lanes * resident;
+      if (score > best * 1.03) {
+        best = score;
+        pick_tw = tw;
+        pick_th = th;
+        pick_warps = nwarps;
+        pick_group = group;
+        pick_smem = bytes;
+        pick_tile = tile_bytes;
+      }
+    }
   }
-  DM_REQUIRE(pick >= 0, "filter layer %d x %d x %d needs more than %zu bytes of shared memory per tile",
-             L.n_in, L.kh, L.kw, (size_t)ctx->smem_optin);
-  a.tw = cand[pick][0];
-  a.th = cand[pick][1];
-  a.pitch = a.tw + L.kw4;
+  DM_REQUIRE(best > 0, "filter layer %d x %d x %d needs more than %zu bytes of shared memory per tile", L.n_in,
+             L.kh, L.kw, (size_t)ctx->smem_optin);
+  a.tw = pick_tw;
+  a.th = pick_th;
+  a.pitch = a.tw + 4 * L.nchunks;
   a.rows = a.th + L.kh - 1;
-  const int items = L.n_out * (a.tw / kSubW) * (a.th / kSubH);
-  const int rounds = (items + 15) / 16;
-  const int nwarps = (items + rounds - 1) / rounds;
-  DM_CUDA(cudaFuncSetAttribute(conv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  a.group = pick_group;
+  a.tile_floats = (int)(pick_tile / 4);
+  DM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pick_smem));
   dim3 grid((a.wout + a.tw - 1) / a.tw, (a.hout + a.th - 1) / a.th, n_img);
-  conv_tile_kernel<<<grid, nwarps * 32, smem, ctx->stream>>>(a);
+  if (L.taps == 5)
+    conv_tile_kernel<5><<<grid, pick_warps * 32, pick_smem, ctx->stream>>>(a);
+  else
+    conv_tile_kernel<4><<<grid, pick_warps * 32, pick_smem, ctx->stream>>>(a);
   count_launch(ctx);
   return DM_OK;
 }
@@ -207,10 +292,12 @@ int dm_filter_create(dm_ctx *ctx, const dm_conv_layer *layers, int n_layers, dm_
     L.n_out = l.n_out;
     L.kh = l.kh;
     L.kw = l.kw;
-    L.kw4 = (l.kw + 3) & ~3;
+    L.taps = l.kw == 5 ? 5 : 4;
+    L.nchunks = L.taps == 5 ? 1 : (l.kw + 3) / 4;
+    L.rowlen = L.taps == 5 ? 6 : 4 * L.nchunks;
     L.n_conn = nc;
     L.tanh_after = l.tanh_after;
-    offs[i].weight = reserve((size_t)nc * L.kh * L.kw4 * 4);
+    offs[i].weight = reserve((size_t)nc * (L.kh + 1) * L.rowlen * 2 * 4);
     offs[i].bias = reserve((size_t)L.n_out * 4);
     offs[i].row_ptr = reserve((size_t)(L.n_out + 1) * 4);
     offs[i].from = reserve((size_t)nc * 4);
@@ -231,13 +318,19 @@ int dm_filter_create(dm_ctx *ctx, const dm_conv_layer *layers, int n_layers, dm_
         }
         if (to != o) continue;
         fr[slot] = from;
-        for (int ky = 0; ky < L.kh; ++ky)
-          memcpy(wdst + ((size_t)slot * L.kh + ky) * L.kw4, l.weight + ((size_t)e * L.kh + ky) * L.kw,
-                 (size_t)L.kw * 4);
+        const float *wsrc = l.weight + (size_t)e * L.kh * L.kw;
+        for (int ky = 0; ky <= L.kh; ++ky)
+          for (int kx = 0; kx < L.kw; ++kx) {
+            float *pair = wdst + (((size_t)slot * (L.kh + 1) + ky) * L.rowlen + kx) * 2;
+            pair[0] = ky < L.kh ? wsrc[ky * L.kw + kx] : 0.0f;
+            pair[1] = ky >= 1 ? wsrc[(ky - 1) * L.kw + kx] : 0.0f;
+          }
         ++slot;
       }
     }
     rp[L.n_out] = slot;
+    for (int o = 0; o < L.n_out; ++o) L.max_conn_per_out = std::max(L.max_conn_per_out, rp[o + 1] - rp[o]);
+    if (L.max_conn_per_out < 1) L.max_conn_per_out = 1;
     prev_out = l.n_out;
     f->layers.push_back(L);
   }

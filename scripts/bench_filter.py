@@ -46,6 +46,9 @@ def main():
     rng = np.random.default_rng(0)
     g = dm.Geometry(layers=[[3, 5, 5, 8], [4, 16, 16, 10]])
     x = torch.rand((2, 3, 360, 640), device="cuda")
+    if "--one" in sys.argv:  # a short run for ncu
+        run("same, 16 pairs", dm.getFilter(g, rng), torch.rand((32, 3, 360, 640), device="cuda"), iters=2)
+        return
     run("c1 {3,5,5,8} tanh {4,16,16,10} map", dm.getFilter(g, rng), x)
     run("same, 16 pairs", dm.getFilter(g, rng), torch.rand((32, 3, 360, 640), device="cuda"))
     run("c3 {3,5,5,10}", dm.getFilter(dm.Geometry(layers=[[3, 5, 5, 10]]), rng), x)
