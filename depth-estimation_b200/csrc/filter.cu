@@ -12,6 +12,8 @@
 // 4-tap chunk it reads 8 floats (two conflict-free LDS.128) and feeds 64 FMAs; the 4-tap weight
 // vectors are warp-uniform (one broadcast LDG.128 each, L1-resident).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "dm_common.cuh"
@@ -89,7 +91,8 @@ __global__ void conv_tile_kernel(const ConvArgs a) {
   const int ox0 = blockIdx.x * a.tw, oy0 = blockIdx.y * a.th;
   const int plane_s = a.rows * a.pitch;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  {  // input footprint of every plane, zero padding materialised; one warp per row
+  {  // input footprint of every plane, zero padding materialised (cp.async zero-fill); one
+     // warp per row, every copy in flight before anybody waits
     const float *src = a.in + (size_t)img * a.n_in * a.h * a.w;
     const int nrows = a.n_in * a.rows;
     for (int row = warp; row < nrows; row += nwarps) {
@@ -97,10 +100,13 @@ __global__ void conv_tile_kernel(const ConvArgs a) {
       const int iy = oy0 - a.pad_t + r;
       const bool row_ok = iy >= 0 && iy < a.h;
       const float *s = src + ((size_t)c * a.h + (row_ok ? iy : 0)) * a.w;
-      float *d = tile + row * a.pitch;
+      const uint32_t d = smem_u32(tile + row * a.pitch);
       for (int x = lane; x < a.pitch; x += 32) {
         const int ix = ox0 - a.pad_l + x;
-        d[x] = (row_ok && ix >= 0 && ix < a.w) ? __ldg(s + ix) : 0.0f;
+        const bool ok = row_ok && ix >= 0 && ix < a.w;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4 * x), "l"(s + (ok ? ix : 0)),
+                     "r"(ok ? 4 : 0)
+                     : "memory");
       }
     }
   }
@@ -115,9 +121,11 @@ __global__ void conv_tile_kernel(const ConvArgs a) {
     __syncthreads();  // the previous phase is done with the weight stage
     {
       const float4 *src = reinterpret_cast<const float4 *>(a.weight) + (size_t)c0 * (wconn / 2);
-      float4 *dst = reinterpret_cast<float4 *>(wsm);
+      const uint32_t dst = smem_u32(wsm);
       const int n4 = (c1 - c0) * (wconn / 2);
-      for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+      for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + i) : "memory");
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");  // the tile's copies too
     }
     __syncthreads();
     const int n_items = (g1 - g0) * subs;
@@ -189,14 +197,19 @@ static int launch_layer(dm_ctx *ctx, const dm_filter::Layer &L, const float *in,
   const void *kernel = L.taps == 5 ? (const void *)conv_tile_kernel<5> : (const void *)conv_tile_kernel<4>;
   // Tile shape and output planes per weight phase: the combination that wastes the least of
   // the machine (partial last wave, outputs past the edge, idle warps in a round, too few
-  // resident warps), among those whose input footprint + weight stage fit in shared memory.
+  // resident warps, halo re-reads, weight phases), among those whose input footprint + weight
+  // stage fit in shared memory.  Weights of the terms fitted on c1's two layers (DM_CONV_TILE
+  // sweeps, scripts/bench_filter.py).
   const int cand[4][2] = {{64, 32}, {64, 16}, {32, 32}, {32, 16}};
   const size_t out_bytes = (size_t)L.max_conn_per_out * (L.kh + 1) * L.rowlen * 8;  // weights of one plane
   double best = -1.0;
   int pick_tw = 0, pick_th = 0, pick_warps = 0, pick_group = 0;
   size_t pick_smem = 0, pick_tile = 0;
+  int force_tile = -1, force_target = 0;  // DM_CONV_TILE="<candidate 0-3>,<CTAs per SM 1-2>": tuning only
+  if (const char *f = getenv("DM_CONV_TILE")) sscanf(f, "%d,%d", &force_tile, &force_target);
   for (int i = 0; i < 4; ++i) {
     for (int per_sm_target = 2; per_sm_target >= 1; --per_sm_target) {
+      if (force_tile >= 0 && (i != force_tile || per_sm_target != force_target)) continue;
       const int tw = cand[i][0], th = cand[i][1];
       const size_t tile_bytes = (size_t)L.n_in * (th + L.kh - 1) * (tw + 4 * L.nchunks) * 4;
       const size_t budget = per_sm_target == 1 ? ctx->smem_optin : (ctx->smem_optin + 1024) / 2 - 1024;
@@ -205,33 +218,39 @@ static int launch_layer(dm_ctx *ctx, const dm_filter::Layer &L, const float *in,
       const size_t bytes = tile_bytes + group * out_bytes;
       const int subs = (tw / kSubW) * (th / kSubH);
       const int items = group * subs;
-      const int rounds = (items + kMaxConvWarps - 1) / kMaxConvWarps;
-      const int nwarps = (items + rounds - 1) / rounds;
+      const int min_rounds = (items + kMaxConvWarps - 1) / kMaxConvWarps;
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
         continue;
-      int per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nwarps * 32, bytes) != cudaSuccess ||
-          per_sm < 1)
-        continue;
-      const long long ctas = (long long)((a.wout + tw - 1) / tw) * ((a.hout + th - 1) / th) * n_img;
-      const long long slots = (long long)per_sm * ctx->num_sms;
-      const long long waves = (ctas + slots - 1) / slots;
-      const double fill = (double)ctas / (double)(waves * slots);                      // last wave
-      const double edge = (double)a.wout * a.hout * n_img / ((double)ctas * tw * th);  // past the edge
-      int total_rounds = 0;
-      for (int g0 = 0; g0 < L.n_out; g0 += group)
-        total_rounds += (std::min(group, L.n_out - g0) * subs + nwarps - 1) / nwarps;
-      const double lanes = (double)L.n_out * subs / ((double)total_rounds * nwarps);   // idle warps
-      const double resident = std::min(1.0, per_sm * nwarps / 16.0);                   // latency hiding
-      const double score = fill * edge * lanes * resident;
-      if (score > best * 1.03) {
-        best = score;
-        pick_tw = tw;
-        pick_th = th;
-        pick_warps = nwarps;
-        pick_group = group;
-        pick_smem = bytes;
-        pick_tile = tile_bytes;
+      for (int rounds = min_rounds; rounds <= min_rounds + 2 && rounds <= items; ++rounds) {
+        const int nwarps = (items + rounds - 1) / rounds;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nwarps * 32, bytes) != cudaSuccess ||
+            per_sm < 1)
+          continue;
+        const long long ctas = (long long)((a.wout + tw - 1) / tw) * ((a.hout + th - 1) / th) * n_img;
+        const long long slots = (long long)per_sm * ctx->num_sms;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double fill = (double)ctas / (double)(waves * slots);                      // last wave
+        const double edge = (double)a.wout * a.hout * n_img / ((double)ctas * tw * th);  // past the edge
+        int total_rounds = 0;
+        for (int g0 = 0; g0 < L.n_out; g0 += group)
+          total_rounds += (std::min(group, L.n_out - g0) * subs + nwarps - 1) / nwarps;
+        const double lanes = (double)L.n_out * subs / ((double)total_rounds * nwarps);   // idle warps
+        const double resident = std::min(1.0, per_sm * nwarps / 16.0);                   // latency hiding
+        const double overlap = per_sm >= 2 ? 1.0 : 0.97;  // a second CTA computes during the tile load
+        const double halo = (double)tw * th / ((double)(tw + 4 * L.nchunks) * (th + L.kh - 1));
+        const int phases = (L.n_out + group - 1) / group;  // each one: barrier + weight reload
+        const double score = fill * edge * lanes * resident * overlap * (0.75 + 0.25 * halo) *
+                             (1.0 - 0.04 * (phases - 1));
+        if (score > best * 1.03) {
+          best = score;
+          pick_tw = tw;
+          pick_th = th;
+          pick_warps = nwarps;
+          pick_group = group;
+          pick_smem = bytes;
+          pick_tile = tile_bytes;
+        }
       }
     }
   }

@@ -60,6 +60,21 @@ int dm_radial_depth(dm_ctx *ctx, const float *flow, int h, int w, float mh, floa
                     float *ret, float *conf);
 int dm_depth_from_xflow(dm_ctx *ctx, const float *xflow, const float *mask, int h, int w, float m,
                         float *depth, float *conf);
+typedef struct dm_conv_layer {
+  int32_t n_in, n_out, kh, kw;
+  int32_t n_conn;
+  int32_t tanh_after;
+  const int32_t *conn;
+  const float *weight;
+  const float *bias;
+} dm_conv_layer;
+typedef struct dm_filter dm_filter;
+int dm_filter_create(dm_ctx *ctx, const dm_conv_layer *layers, int n_layers, dm_filter **out);
+int dm_filter_destroy(dm_filter *filter);
+int dm_filter_output_size(const dm_filter *filter, int h, int w, int pad_l, int pad_r, int pad_t,
+                          int pad_b, int *channels, int *hout, int *wout);
+int dm_filter_forward(dm_ctx *ctx, const dm_filter *filter, const float *in, int n_img, int h, int w,
+                      int pad_l, int pad_r, int pad_t, int pad_b, float *out);
 ]]
 
 local M = {}

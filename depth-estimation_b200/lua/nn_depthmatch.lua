@@ -170,3 +170,56 @@ function radial(geometry, flow, mh, mw)
                               torch.data(ret), torch.data(conf)))
    return ret, conf
 end
+
+-- ---------------------------------------------------------------- feature extractor
+-- nn.FilterGPU(filter): wraps the nn.Sequential getFilter(geometry) returns
+-- (opticalflow_model.lua:45-79) -- the weights stay where load/saveWeights put them, the
+-- forward pass of both patches runs on the GPU.  Call :sync() after changing weights.
+local FilterGPU, fparent = torch.class('nn.FilterGPU', 'nn.Module')
+function FilterGPU:__init(filter)
+   fparent.__init(self)
+   self.filter = filter
+   self.pads = {0, 0, 0, 0}     -- l, r, t, b: the nn.SpatialZeroPadding of getMultiscalePrefilter
+   self:sync()
+end
+function FilterGPU:sync()
+   local mods, layers, keep = self.filter.modules, {}, {}
+   for i = 1,#mods do
+      local m = mods[i]
+      if torch.typename(m) == 'nn.Tanh' then
+         layers[#layers].tanh_after = 1
+      else
+         local l = {n_in = m.nInputPlane, n_out = m.nOutputPlane, kh = m.kH, kw = m.kW, n_conn = 0, tanh_after = 0,
+                    weight = m.weight:contiguous(), bias = m.bias:contiguous()}
+         if m.connTable then
+            l.conn = m.connTable:int():contiguous()
+            l.n_conn = l.conn:size(1)
+         end
+         table.insert(layers, l)
+      end
+   end
+   local arr = ffi.new('dm_conv_layer[?]', #layers)
+   for i, l in ipairs(layers) do
+      local a = arr[i-1]
+      a.n_in, a.n_out, a.kh, a.kw, a.n_conn, a.tanh_after = l.n_in, l.n_out, l.kh, l.kw, l.n_conn, l.tanh_after
+      a.weight, a.bias = torch.data(l.weight), torch.data(l.bias)
+      a.conn = l.conn and torch.data(l.conn) or nil
+   end
+   local h = ffi.new('dm_filter*[1]')
+   dm.check(C.dm_filter_create(ctx, arr, #layers, h))
+   self.handle = ffi.gc(h[0], C.dm_filter_destroy)
+   self.nOut = layers[#layers].n_out
+end
+function FilterGPU:updateOutput(input)           -- input: C x H x W or N x C x H x W
+   local inp = input:contiguous()
+   local n = inp:dim() == 4 and inp:size(1) or 1
+   local h, w = inp:size(inp:dim() - 1), inp:size(inp:dim())
+   local p = self.pads
+   local co, ho, wo = ffi.new('int[1]'), ffi.new('int[1]'), ffi.new('int[1]')
+   dm.check(C.dm_filter_output_size(self.handle, h, w, p[1], p[2], p[3], p[4], co, ho, wo))
+   if inp:dim() == 4 then self.output:resize(n, co[0], ho[0], wo[0]) else self.output:resize(co[0], ho[0], wo[0]) end
+   dm.check(C.dm_filter_forward(ctx, self.handle, torch.data(inp), n, h, w, p[1], p[2], p[3], p[4],
+                                torch.data(self.output)))
+   return self.output
+end
+FilterGPU.updateGradInput = nobackward('nn.FilterGPU')

@@ -28,6 +28,16 @@ def main():
     in1 = in2[:, :, 8:8 + 145, 8:8 + 285] + 0.05 * torch.randn((1, 10, 145, 285), device="cuda", generator=g)
     ms = timed(lambda: dm.match_extract(in1, in2, 17, 17, want=("index", "pmax", "score_thr")))
     res["c1 10x161x301 17x17 (1 pair)"] = {"ms": ms, "pairs_per_s": 1e3 / ms}
+    # c1 from raw frames: 3x180x320 RGB pair -> {3,5,5,8} tanh {4,16,16,10} -> 10x161x301 -> 17x17
+    import numpy as np
+    geo1 = dm.Geometry(layers=[[3, 5, 5, 8], [4, 16, 16, 10]], maxh=17, maxw=17, hImg=180, wImg=320)
+    flt = dm.getFilter(geo1, np.random.default_rng(1))
+    fr = torch.rand((2, 3, 180, 320), device="cuda", generator=g)
+    model1 = dm.getModel(geo1, True, False, fused=True, filter=flt)
+    ms = timed(lambda: model1.forward(dm.prepareInput(geo1, fr[0], fr[1])))
+    res["c1 raw frames 3x180x320: filter + 17x17 match (1 pair)"] = {"ms": ms, "pairs_per_s": 1e3 / ms}
+    ms = timed(lambda: flt.forward(fr))
+    res["c1 filter alone (both frames)"] = {"ms": ms}
     # c2: 64 pairs of 320x180, 33x33
     in2 = torch.randn((64, 10, 180, 320), device="cuda", generator=g)
     in1 = in2[:, :, 16:16 + 148, 16:16 + 288] + 0.05 * torch.randn((64, 10, 148, 288), device="cuda", generator=g)
