@@ -17,3 +17,6 @@ There is no CPU fallback: everything below calls the CUDA library.
 """
 from ._lib import DepthMatchError, load  # noqa: F401
 from .api import *  # noqa: F401,F403
+from . import torch7io  # noqa: F401
+from .model_io import (loadCalibration, loadModel, loadTesterNetwork, loadWeightsFrom,  # noqa: F401
+                       modelDirectory, saveModel, saveNetwork)

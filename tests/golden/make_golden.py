@@ -59,12 +59,29 @@ def inline_vectors():
     np.savez_compressed(os.path.join(HERE, "ref_inline.npz"), **out)
 
 
+def calibration_vectors():
+    """ref_calibration.npz: the four Torch7-serialised calibration tables the reference ships
+    (radial/*.cal, version2/rectified_gopro.cal; written by radial/generate_calibration_file.lua),
+    byte for byte -- fixtures for the torch7io reader/writer."""
+    ref = "/root/reference"
+    out = {}
+    for name, rel in (("ardrone", "radial/ardrone.cal"), ("gopro", "radial/gopro.cal"),
+                      ("rectified_gopro", "radial/rectified_gopro.cal"),
+                      ("rectified_gopro_v2", "version2/rectified_gopro.cal")):
+        out[name] = np.frombuffer(open(os.path.join(ref, rel), "rb").read(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "ref_calibration.npz"), **out)
+
+
 def main():
     assert O.ref() is not None, "build oracle/_ref first (make -C oracle)"
+    if "--calibration-only" in sys.argv:
+        calibration_vectors()
+        return
     if "--inline-only" in sys.argv:
         inline_vectors()
         return
     inline_vectors()
+    calibration_vectors()
     rng = np.random.default_rng(20261018)
 
     # ---- reference native code: extractOutput / extractOutputMarginalized

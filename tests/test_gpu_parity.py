@@ -687,3 +687,27 @@ def test_multiscale_prefilter_and_raw_frames_end_to_end(dm, oracle):
     assert bad.sum() == 0
     dy, dx = dm.x2yx(g1, got.reshape(f1.shape[1:]))
     assert np.median(dy) - 5 == -2 and np.median(dx) - 5 == 2
+
+
+def test_saved_model_loads_and_runs(dm, oracle, tmp_path):
+    """next row 4: saveModel -> loadModel (version-9 Torch7 table) -> forward gives the flow of
+    the model that was saved (weights travel; the connection table is re-drawn on load, as in the
+    reference, so the second layer is a full convolution here to make the outputs comparable)."""
+    rng = np.random.default_rng(8)
+    g = dm.Geometry(layers=[[3, 5, 5, 6], [6, 7, 7, 10]], maxh=9, maxw=9, maxhHR=9, maxwHR=9, maxhGT=9, maxwGT=9,
+                    hImg=60, wImg=90, output_extraction_method="max")
+    learning = dict(rate=0.01, rate_decay=0, weight_decay=0, first_image=0, delta=1, num_images=2)
+    model = dm.getModel(g, True, False, fused=True, rng=rng)
+    path = dm.saveModel(str(tmp_path), "m", g, learning, model, 1)
+    loaded = dm.loadModel(path, True, False, fused=True, rng=np.random.default_rng(99))
+    # biases are not part of a version-9 file (opticalflow_model_io.lua:151): copy them by hand
+    for a, b in zip(loaded["model"].filter.modules, model.filter.modules):
+        if hasattr(a, "bias"):
+            assert np.array_equal(a.weight, b.weight) and not np.array_equal(a.bias, b.bias)
+            a.bias[...] = b.bias
+    loaded["model"].filter.reset_weights()
+    fr = rng.random((2, 3, 60, 90)).astype(np.float32)
+    want = model.forward(dm.prepareInput(g, fr[0], fr[1]))
+    got = loaded["model"].forward(dm.prepareInput(loaded["geometry"], fr[0], fr[1]))
+    np.testing.assert_array_equal(got["index"], want["index"])
+    np.testing.assert_array_equal(got["pmax"], want["pmax"])
