@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frame pairs per GPU per step")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-volume", action="store_true", help="skip the volume-mode side measurement")
     args = ap.parse_args()
@@ -296,22 +296,36 @@ def main():
               "score_thr": ((B, H1, W1), torch.float32), "flow_full": ((B, 2, H, W), torch.float32)}
     out_p = {k: torch.empty(shp, dtype=dt).pin_memory().numpy() for k, (shp, dt) in shapes.items()}
 
-    def e2e_step():
-        return dm.match_extract(in1_p, f2_pn, MAXH, MAXW, canvas=(H, W), want=want, ctx=ctx, out=out_p)
+    # Two contexts alternate so that the H2D of step i+1 overlaps the kernels and the D2H of step
+    # i (DM_FLAG_ASYNC: the call returns once queued; a context is synchronised before its
+    # buffers are reused, and both before the clock stops).  Every step copies its inputs in and
+    # its results out.
+    ctxs = [ctx, dm.Context(torch.cuda.current_device())]
+    outs = [out_p, {k: torch.empty(shp, dtype=dt).pin_memory().numpy() for k, (shp, dt) in shapes.items()}]
 
-    e2e_step()
+    def e2e_step(i):
+        c = ctxs[i % 2]
+        c.synchronize()
+        return dm.match_extract(in1_p, f2_pn, MAXH, MAXW, canvas=(H, W), want=want, ctx=c, out=outs[i % 2],
+                                async_=True)
+
+    for i in range(2):
+        e2e_step(i)
+    for c in ctxs:
+        c.synchronize()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        r = e2e_step()
+    for i in range(args.e2e_steps):
+        r = e2e_step(i)
+    for c in ctxs:
+        c.synchronize()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * B * args.e2e_steps / float(te.item())
-    span1 = (B - 1) * C * H * W + (C - 1) * H * W + (H1 - 1) * W + W1
-    h2d = 4 * (span1 + B * C * H * W)
+    h2d = 4 * (B * C * H1 * W1 + B * C * H * W)   # the frame-1 crop is packed by a 3-D copy
     d2h = B * (H1 * W1 * (8 + 4 + 4) + 2 * H * W * 4)
 
     if rank != 0:

@@ -239,6 +239,8 @@ int dm_destroy(dm_ctx *ctx) {
 int dm_synchronize(dm_ctx *ctx) {
   DM_REQUIRE(ctx != nullptr, "dm_synchronize: ctx is NULL");
   DM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 2; ++i)  // chunks of a DM_FLAG_ASYNC host-buffer call still in flight
+    if (ctx->pipe[i]) DM_CUDA(cudaStreamSynchronize(ctx->pipe[i]->stream));
   return DM_OK;
 }
 
@@ -269,7 +271,13 @@ int dm_host_free(void *ptr) {
   return DM_OK;
 }
 
-int64_t dm_launch_count(dm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t dm_launch_count(dm_ctx *ctx) {
+  if (!ctx) return 0;
+  int64_t n = ctx->launches;
+  for (int i = 0; i < 2; ++i)
+    if (ctx->pipe[i]) n += ctx->pipe[i]->launches;
+  return n;
+}
 
 int dm_set_profiling(dm_ctx *ctx, int on) {
   DM_REQUIRE(ctx != nullptr, "dm_set_profiling: ctx is NULL");

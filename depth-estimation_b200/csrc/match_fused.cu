@@ -606,9 +606,30 @@ static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, int tile_r
   const float *d1 = in->in1;
   if (classify(in->in1) == PtrKind::Host) {
     const size_t span = (size_t)((g.N - 1) * s1n + (g.C - 1) * s1c + (g.H1 - 1) * s1y + g.W1);
-    const void *p = nullptr;
-    DM_CHECK(call.in(in->in1, span * sizeof(float), &p));
-    d1 = static_cast<const float *>(p);
+    const size_t dense = (size_t)g.N * g.C * g.H1 * g.W1;
+    if (span > dense + dense / 32 && s1y >= g.W1 && s1c % s1y == 0 && s1c / s1y >= g.H1 &&
+        s1n == (long long)g.C * s1c) {
+      // a cropped view (prepareInput's narrow): one 3-D copy moves only the rows of the crop
+      // over PCIe and packs them
+      void *buf = nullptr;
+      DM_CHECK(call.alloc(&buf, dense * sizeof(float)));
+      cudaMemcpy3DParms cp = {};
+      cp.srcPtr = make_cudaPitchedPtr(const_cast<float *>(in->in1), (size_t)s1y * sizeof(float),
+                                      (size_t)g.W1, (size_t)(s1c / s1y));
+      cp.dstPtr = make_cudaPitchedPtr(buf, (size_t)g.W1 * sizeof(float), (size_t)g.W1, (size_t)g.H1);
+      cp.extent = make_cudaExtent((size_t)g.W1 * sizeof(float), (size_t)g.H1, (size_t)g.N * g.C);
+      cp.kind = cudaMemcpyHostToDevice;
+      DM_CUDA(cudaMemcpy3DAsync(&cp, ctx->stream));
+      ctx->call_has_host = true;
+      d1 = static_cast<const float *>(buf);
+      s1y = g.W1;
+      s1c = (long long)g.H1 * g.W1;
+      s1n = (long long)g.C * s1c;
+    } else {
+      const void *p = nullptr;
+      DM_CHECK(call.in(in->in1, span * sizeof(float), &p));
+      d1 = static_cast<const float *>(p);
+    }
   }
   g.in1 = d1;
   g.s1n = s1n;
@@ -854,8 +875,9 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
   const bool host_in = in->in1 && in->in2 && classify(in->in1) == PtrKind::Host &&
                        classify(in->in2) == PtrKind::Host;
   const int N = in->n_pairs;
+  const bool async = (flags & DM_FLAG_ASYNC) != 0;  // the caller waits with dm_synchronize()
   if (!host_in || N < 4 || ctx->is_child || getenv("DM_NO_PIPELINE"))
-    return match_extract_impl(ctx, in, maxh, maxw, flags, prob_threshold, h_img, w_img, out, false);
+    return match_extract_impl(ctx, in, maxh, maxw, flags, prob_threshold, h_img, w_img, out, async);
   for (int i = 0; i < 2; ++i)
     if (!ctx->pipe[i]) {
       DM_CHECK(dm_create(ctx->device, &ctx->pipe[i]));
@@ -890,11 +912,9 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
     rc = match_extract_impl(ctx->pipe[c & 1], &sub, maxh, maxw, flags, prob_threshold, h_img, w_img, &so,
                             true);
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 2 && !async; ++i) {
     cudaError_t e = cudaStreamSynchronize(ctx->pipe[i]->stream);
     if (e != cudaSuccess && rc == DM_OK) rc = cuda_fail(e, "pipeline synchronize", __FILE__, __LINE__);
-    ctx->launches += ctx->pipe[i]->launches;
-    ctx->pipe[i]->launches = 0;
   }
   return rc;
 }

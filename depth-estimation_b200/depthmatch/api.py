@@ -11,7 +11,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import (DM_FLAG_EXACT_SSD, DM_FLAG_TIE_MIDDLE, DM_VOLUME_EXACT, DM_VOLUME_NEG_SOFTMAX,
+from ._lib import (DM_FLAG_ASYNC, DM_FLAG_EXACT_SSD, DM_FLAG_TIE_MIDDLE, DM_VOLUME_EXACT, DM_VOLUME_NEG_SOFTMAX,
                    DM_VOLUME_SSD, DepthMatchError, check, dm_extract_out, dm_pair)
 
 __all__ = [
@@ -200,11 +200,13 @@ def match_volume(in1, in2, maxh, maxw, softmax=False, exact=False, ctx=None):
 
 def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_threshold=0.11,
                   canvas=None, want=("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx"),
-                  ctx=None, out=None):
+                  ctx=None, out=None, async_=False):
     """Fused prepareInput-less forward + processOutput.  Returns a dict of arrays, each
     [N,]H1,W1 (soft_yx: [N,]2,H1,W1; flow_full: [N,]2,hImg,wImg when canvas=(hImg,wImg)).
     `out` may hold preallocated result buffers by name (e.g. pinned host memory), with the
-    batched shapes [N,...]; they are written in place and returned."""
+    batched shapes [N,...]; they are written in place and returned.
+    async_=True (host buffers, preallocated `out`): returns once the work is queued; the inputs
+    and `out` belong to the library until ctx.synchronize()."""
     args = _Args(ctx)
     single = (in1.dim() if _is_torch(in1) else np.ndim(in1)) == 3
     p, a, b = _pair_struct(args, in1, in2)
@@ -236,12 +238,26 @@ def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_thres
         setattr(o, name, ptr)
         res[name] = arr
     flags = (DM_FLAG_TIE_MIDDLE if tie_middle else 0) | (DM_FLAG_EXACT_SSD if exact else 0)
+    if async_:
+        if out is None or any(n not in out for n in want) or not _caller_owned_host(in1, a, in2, b):
+            raise DepthMatchError(_lib.DM_ERR_INVALID, "async_ needs caller-owned `out` buffers for every "
+                                  "requested result and inputs that need no conversion copy")
+        flags |= DM_FLAG_ASYNC
     himg, wimg = (int(canvas[0]), int(canvas[1])) if canvas is not None else (H1, W1)
     check(c._lib.dm_match_extract(c.handle, C.byref(p), maxh, maxw, flags, float(prob_threshold),
                                   himg, wimg, C.byref(o)))
     if single:
         res = {k: v[0] for k, v in res.items()}
     return res
+
+
+def _caller_owned_host(in1, a, in2, b):
+    """True when the staged views a, b are the caller's own host memory (no conversion copy that
+    would be freed while an asynchronous call still reads it)."""
+    for x, v in ((in1, a), (in2, b)):
+        if not isinstance(x, np.ndarray) or not isinstance(v, np.ndarray) or not np.shares_memory(x, v):
+            return False
+    return True
 
 
 # ------------------------------------------------------------------ geometry

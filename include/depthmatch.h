@@ -99,6 +99,9 @@ int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, int mode
 /* ---- K1+K2 fused: match + extract, volume never written ------------------ */
 #define DM_FLAG_TIE_MIDDLE 1u  /* zero-flow tie rule, opticalflow_model.lua:157-159 */
 #define DM_FLAG_EXACT_SSD 2u   /* unfused mul+add (bit-exact with the CPU path) instead of FMA */
+#define DM_FLAG_ASYNC 4u       /* host-buffer call: return once the copies and kernels are queued;
+                                  inputs and outputs belong to the library until dm_synchronize(ctx).
+                                  Page-locked buffers (dm_host_alloc) make the copies overlap. */
 
 typedef struct dm_extract_out {
   /* every pointer may be NULL = not wanted.  Shapes are [n_pairs][h1][w1] unless noted. */

@@ -711,3 +711,28 @@ def test_saved_model_loads_and_runs(dm, oracle, tmp_path):
     got = loaded["model"].forward(dm.prepareInput(loaded["geometry"], fr[0], fr[1]))
     np.testing.assert_array_equal(got["index"], want["index"])
     np.testing.assert_array_equal(got["pmax"], want["pmax"])
+
+
+def test_async_host_call_and_cropped_view_equal_the_synchronous_call(dm):
+    """DM_FLAG_ASYNC (results valid after ctx.synchronize()) and the packed 3-D copy of a cropped
+    frame-1 view give exactly what the plain call gives."""
+    import torch
+    rng = np.random.default_rng(17)
+    N, C, H, W, mh = 8, 4, 40, 56, 9
+    f2 = torch.from_numpy(rng.standard_normal((N, C, H, W)).astype(np.float32)).pin_memory().numpy()
+    f1 = torch.from_numpy(rng.standard_normal((N, C, H, W)).astype(np.float32)).pin_memory().numpy()
+    in1 = f1[:, :, 4:4 + H - mh + 1, 4:4 + W - mh + 1]          # prepareInput's narrow: a strided view
+    want = ("index", "pmax", "score_thr")
+    ref = dm.match_extract(np.ascontiguousarray(in1), f2, mh, mh, want=want)
+    ctx = dm.Context(0)
+    out = {k: torch.empty(tuple(v.shape), dtype=torch.from_numpy(v).dtype).pin_memory().numpy()
+           for k, v in ref.items()}
+    for k in out:
+        out[k][...] = 0
+    res = dm.match_extract(in1, f2, mh, mh, want=want, ctx=ctx, out=out, async_=True)
+    ctx.synchronize()
+    for k in want:
+        np.testing.assert_array_equal(res[k], ref[k])
+    with pytest.raises(dm.DepthMatchError):      # a conversion copy would not outlive the call
+        dm.match_extract(in1.astype(np.float64), f2, mh, mh, want=want, ctx=ctx, out=out, async_=True)
+    assert ctx.launch_count() > 0
