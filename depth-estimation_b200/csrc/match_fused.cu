@@ -16,6 +16,7 @@
 // probabilities agree with the two-pass CPU path to ~1e-6 relative, not bit-wise.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "match_kernels.cuh"
 
@@ -46,6 +47,12 @@ struct ExtractParams {
   unsigned *todo_mask;  // [todo slot][nwords]
   unsigned *ntodo;
   float *vmin, *vinv;   // per-pixel min and 1/sum for the exact pass
+  // kDot / kFma twin launch: both kernels read the largest |a|^2 and |b|^2 the norm pre-pass
+  // found and only the one the bound selects runs (the other returns at once)
+  const unsigned *stats;  // {max |a|^2, max |b|^2} as float bits; NULL: run unconditionally
+  float dot_limit;        // kDot is taken when max |a|^2 + max |b|^2 <= dot_limit
+  const float *in2;       // frame 2 as the kernels address it, for the exact re-score of the winner
+  long long s2n, s2c, s2y;
 };
 
 // Per-thread state of the fused reduction: for each of the thread's kP pixels the running
@@ -65,6 +72,8 @@ struct ExtractEpi {
   int vfrom[kP];
   unsigned *mask;  // [nwords][kP][kCThreads] words, this thread's column
   float *vmid;     // [kP][kCThreads]
+  float mexact[kP];  // kDot: the winner's SSD re-scored in the difference form
+  bool rescored = false;
 
   __device__ ExtractEpi(const ExtractParams &p, unsigned *smem_extra)
       : P(p), mask(smem_extra + threadIdx.x) {
@@ -194,6 +203,30 @@ struct ExtractEpi {
     }
   }
 
+  // kDot: min_ssd is reported from the difference form (the dot form cancels: a perfect match
+  // would read a few ulp of |a|^2 + |b|^2 instead of 0).  a2 holds -2a.
+  template <int CT>
+  __device__ __forceinline__ void tile_rescore(const float2 (&a2)[CT][2], int n, int y, int x0) {
+    rescored = true;
+    if (!P.min_ssd || y >= P.g.H1) return;
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      mexact[p] = 0.0f;
+      if (x0 + p >= P.g.W1) continue;
+      const int dy = (idx[p] - 1) / P.g.maxw, dx = (idx[p] - 1) % P.g.maxw;
+      const float *b = P.in2 + (long long)n * P.s2n + (long long)(y + dy) * P.s2y + (x0 + p + dx);
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        const float2 av = a2[k][p >> 1];
+        const float a = -0.5f * ((p & 1) ? av.y : av.x);
+        const float d = a - (k < P.g.Cin ? __ldg(b + (long long)k * P.s2c) : 0.0f);
+        acc = fmaf(d, d, acc);
+      }
+      mexact[p] = acc;
+    }
+  }
+
   __device__ __forceinline__ void tile_end(int n, int y, int x0) {
     const SweepGeom &g = P.g;
     if (y >= g.H1) return;
@@ -210,7 +243,7 @@ struct ExtractEpi {
         if (emid * inv == inv) win = P.middle;  // p[middle] == max p (opticalflow_model.lua:157-159)
       }
       if (P.index) P.index[o] = win;
-      if (P.min_ssd) P.min_ssd[o] = m[p];
+      if (P.min_ssd) P.min_ssd[o] = rescored ? mexact[p] : m[p];
       if (P.pmax) P.pmax[o] = inv;
       if (SOFT && P.soft_yx) {
         const size_t plane = (size_t)g.H1 * g.W1;
@@ -259,15 +292,20 @@ struct ExtractEpi {
   }
 };
 
-template <int CT, bool EXACT, bool SOFT>
+template <int CT, int MODE, bool SOFT>
 __global__ void __launch_bounds__(ExtractCfg::kThreads, 1)
-match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const ExtractParams P) {
+match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_nb,
+                     const ExtractParams P) {
+  if (P.stats) {  // twin launch: the norm bound picks the dot or the difference form
+    const bool dot_ok = __uint_as_float(P.stats[0]) + __uint_as_float(P.stats[1]) <= P.dot_limit;
+    if (dot_ok != (MODE == kDot)) return;
+  }
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ring = reinterpret_cast<float *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)P.g.nslot * P.g.slab_floats);
   unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
   ExtractEpi<SOFT> epi(P, extra);
-  run_sweep<ExtractCfg, CT, EXACT>(&tmap, P.g, ring, full, epi);
+  run_sweep<ExtractCfg, CT, MODE>(&tmap, &tmap_nb, P.g, ring, full, epi);
 }
 
 // ---------------------------------------------------------------- exact threshold pass
@@ -546,7 +584,7 @@ match_volume_kernel(const __grid_constant__ CUtensorMap tmap, const VolumeParams
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)P.g.nslot * P.g.slab_floats);
   float *stg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
   VolumeEpi epi(P, stg);
-  run_sweep<VolumeCfg, CT, EXACT>(&tmap, P.g, ring, full, epi);
+  run_sweep<VolumeCfg, CT, EXACT ? kExact : kFma>(&tmap, &tmap, P.g, ring, full, epi);
 }
 
 // ---------------------------------------------------------------- host side
@@ -719,14 +757,36 @@ static int fit_ring(dm_ctx *ctx, SweepGeom *g, int tile_rows, int max_slots, siz
   return DM_OK;
 }
 
-static const void *pick_extract(int CT, bool exact, bool soft) {
-#define DM_PICK(ct)                                                                             \
-  (exact ? (soft ? (const void *)match_extract_kernel<ct, true, true>                            \
-                 : (const void *)match_extract_kernel<ct, true, false>)                          \
-         : (soft ? (const void *)match_extract_kernel<ct, false, true>                           \
-                 : (const void *)match_extract_kernel<ct, false, false>))
+static const void *pick_extract(int CT, int mode, bool soft) {
+#define DM_PICK2(ct, md)                                                   \
+  (soft ? (const void *)match_extract_kernel<ct, md, true> : (const void *)match_extract_kernel<ct, md, false>)
+#define DM_PICK(ct) (mode == kExact ? DM_PICK2(ct, kExact) : (mode == kDot ? DM_PICK2(ct, kDot) : DM_PICK2(ct, kFma)))
   return CT == 4 ? DM_PICK(4) : (CT == 10 ? DM_PICK(10) : DM_PICK(16));
 #undef DM_PICK
+#undef DM_PICK2
+}
+
+// |x|^2 per pixel over the channels (one FMA chain, k ascending -- the sweep computes |a|^2 the
+// same way) and the largest one, for the kDot bound.  out may be NULL (only the maximum).
+__global__ void norm_kernel(const float *in, long long sn, long long sc, long long sy, int N, int C, int H,
+                            int W, float *out, long long on, long long oy, unsigned *stat) {
+  float mx = 0.0f;
+  const long long total = (long long)N * H * W;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % W), y = (int)((t / W) % H), n = (int)(t / ((long long)W * H));
+    const float *src = in + n * sn + y * sy + x;
+    float s = 0.0f;
+    for (int k = 0; k < C; ++k) {
+      const float v = __ldg(src + k * sc);
+      s = fmaf(v, v, s);
+    }
+    if (out) out[n * on + y * oy + x] = s;
+    mx = fmaxf(mx, s);   // NaN inputs: fmaxf drops them here, the SSDs are NaN in either form
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(stat, __float_as_uint(mx));
 }
 
 static int grid_for(dm_ctx *ctx, const void *kernel, int threads, size_t smem, int ntiles) {
@@ -829,18 +889,66 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     DM_CUDA(cudaMemsetAsync(P.ntodo, 0, sizeof(unsigned), ctx->stream));
   }
   const size_t extra = kBarBytes + (size_t)(P.nwords + 1) * ExtractCfg::kCThreads * kP * sizeof(unsigned);
-  DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
-  const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
   const bool exact = flags & DM_FLAG_EXACT_SSD;
-  const void *kfn = nullptr;
-  kfn = pick_extract(pr.CT, exact, P.soft_yx != nullptr);
-  DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, g.ntiles);
-  void *args[] = {(void *)&pr.tmap, (void *)&P};
-  prof_begin(ctx);
-  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(ExtractCfg::kThreads), args, smem, ctx->stream));
-  prof_end(ctx);
-  count_launch(ctx);
+  P.stats = nullptr;
+  P.dot_limit = 0.0f;
+  P.in2 = pr.in2_dev;
+  P.s2n = pr.s2n;
+  P.s2c = pr.s2c;
+  P.s2y = pr.s2y;
+  DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
+  auto launch = [&](const ExtractParams &Q, const CUtensorMap &nbmap, int mode) -> int {
+    const size_t smem = ring_bytes(Q.g, Q.g.nslot) + extra;
+    const void *kfn = pick_extract(pr.CT, mode, Q.soft_yx != nullptr);
+    DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, Q.g.ntiles);
+    void *args[] = {(void *)&pr.tmap, (void *)&nbmap, (void *)&Q};
+    DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(ExtractCfg::kThreads), args, smem, ctx->stream));
+    count_launch(ctx);
+    return DM_OK;
+  };
+  // The dot form (|a|^2 + |b|^2 - 2 a.b) halves the FP32 work of the sweep; its absolute error
+  // is a few ulp of |a|^2 + |b|^2.  It is used when the largest norms keep that error under
+  // ~1e-5 (the parity bar on the soft-max scores): a pre-pass writes |b|^2 per frame-2 pixel and
+  // the maxima, then both kernels are launched and the device-side bound lets one of them run.
+  const char *force = getenv("DM_SSD_FORM");  // "diff" / "dot": tuning and tests only
+  const bool allow_dot = !exact && !(flags & DM_FLAG_DIFF_SSD) && !(force && !strcmp(force, "diff"));
+  bool twin = false;
+  ExtractParams Pd = P;
+  CUtensorMap nbmap;
+  if (allow_dot) {
+    Pd.g.nb_off = (Pd.g.C * Pd.g.WB + 31) & ~31;
+    Pd.g.slab_floats = Pd.g.nb_off + ((Pd.g.WB + 31) & ~31);
+    twin = fit_ring(ctx, &Pd.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra) == DM_OK;
+  }
+  if (twin) {
+    const long long w2p = (g.W2 + 3) & ~3LL;
+    void *nbuf = nullptr, *stats = nullptr;
+    DM_CHECK(call.alloc(&nbuf, (size_t)g.N * g.H2 * w2p * sizeof(float)));
+    DM_CHECK(call.alloc(&stats, 256));
+    DM_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned), ctx->stream));
+    const int nthr = 256, nblk = ctx->num_sms * 8;
+    prof_begin(ctx);
+    norm_kernel<<<nblk, nthr, 0, ctx->stream>>>(g.in1, g.s1n, g.s1c, g.s1y, g.N, pr.Cin, g.H1, g.W1, nullptr, 0,
+                                                0, static_cast<unsigned *>(stats));
+    norm_kernel<<<nblk, nthr, 0, ctx->stream>>>(pr.in2_dev, pr.s2n, pr.s2c, pr.s2y, g.N, pr.Cin, g.H2, g.W2,
+                                                static_cast<float *>(nbuf), (long long)g.H2 * w2p, w2p,
+                                                static_cast<unsigned *>(stats) + 1);
+    count_launch(ctx, 2);
+    const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, 1u, (uint64_t)g.N};
+    const uint64_t strides[3] = {(uint64_t)w2p * 4, (uint64_t)g.H2 * w2p * 4, (uint64_t)g.H2 * w2p * 4};
+    const uint32_t box[4] = {(uint32_t)g.WB, 1u, 1u, 1u};
+    DM_CHECK(encode_tensor_map_4d(&nbmap, static_cast<const float *>(nbuf), dims, strides, box));
+    P.stats = Pd.stats = static_cast<const unsigned *>(stats);
+    P.dot_limit = Pd.dot_limit = (force && !strcmp(force, "dot")) ? 3.0e38f : 256.0f;
+    DM_CHECK(launch(Pd, nbmap, kDot));
+    DM_CHECK(launch(P, pr.tmap, kFma));
+    prof_end(ctx);
+  } else {
+    prof_begin(ctx);
+    DM_CHECK(launch(P, pr.tmap, exact ? kExact : kFma));
+    prof_end(ctx);
+  }
   if (want_thr) {
     ThresholdPass T;
     T.in1 = g.in1; T.s1n = g.s1n; T.s1c = g.s1c; T.s1y = g.s1y;
@@ -940,10 +1048,10 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
   const size_t extra = kBarBytes + (size_t)ExtractCfg::kCThreads * kP * sizeof(unsigned);
   DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
   const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
-  const void *kfn = pick_extract(pr.CT, exact, false);
+  const void *kfn = pick_extract(pr.CT, exact ? kExact : kFma, false);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, g.ntiles);
-  void *args[] = {(void *)&pr.tmap, (void *)&P};
+  void *args[] = {(void *)&pr.tmap, (void *)&pr.tmap, (void *)&P};
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(ExtractCfg::kThreads), args, smem, ctx->stream));
   count_launch(ctx);
   return DM_OK;

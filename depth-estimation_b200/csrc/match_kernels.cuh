@@ -69,11 +69,66 @@ struct SweepGeom {
   int tiles_x, tiles_y, ntiles;
   int WB;
   BlockSchedule bs;
-  int slab_floats;  // floats between ring slots: C*WB rounded up to 128 bytes
+  int slab_floats;  // floats between ring slots: C*WB rounded up to 128 bytes (+ the norm row)
+  int nb_off;       // kDot: offset of the |b|^2 row inside a slot (128-byte aligned)
   int nslot;        // ring slots actually used (<= Cfg::kNSlot, >= Cfg::kTH + 2): what fits
   const float *in1;
   long long s1n, s1c, s1y;
 };
+
+// How a sweep kernel forms the SSD.
+//   kFma   (a-b)^2 accumulated with FMA (packed FADD2 + FFMA2), the default for the volume
+//   kExact multiply and add rounded separately: bit-exact with the non-contracting CPU path
+//   kDot   |a|^2 + |b|^2 - 2 a.b: one packed FFMA2 per two terms instead of FADD2 + FFMA2.  The
+//          frame-2 norms come from a small pre-pass through a second TMA box per row; the
+//          absolute error is a few ulp of |a|^2 + |b|^2, so the host only allows it when the
+//          largest norms keep that below the parity bar (see match_extract_impl).
+enum SsdMode { kFma = 0, kExact = 1, kDot = 2 };
+
+// kDot block: acc2[pp][j] = (na_even, na_odd) + nb[col] + sum_k (-2 a[k]) * b[k][col]; `a2`
+// holds -2a.  Same operation sequence for every (pixel, displacement): identical inputs give
+// bit-identical sums, so the ties of flat image regions stay ties.
+template <int CT, int JW>
+__device__ __forceinline__ void dot_block2(const float2 (&a2)[CT][2], const float2 (&na2)[2],
+                                           const float *bsrc, const float *nbsrc, int WB,
+                                           float2 (&acc2)[2][JW]) {
+  constexpr int NBF = JW == kR ? kNB : kP;
+  {
+    float nb[NBF];
+    const float4 *src = reinterpret_cast<const float4 *>(nbsrc);
+#pragma unroll
+    for (int j = 0; j < NBF / 4; ++j) {
+      const float4 t = src[j];
+      nb[4 * j + 0] = t.x;
+      nb[4 * j + 1] = t.y;
+      nb[4 * j + 2] = t.z;
+      nb[4 * j + 3] = t.w;
+    }
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+      for (int j = 0; j < JW; ++j)
+        acc2[pp][j] = __fadd2_rn(na2[pp], make_float2(nb[2 * pp + j], nb[2 * pp + j]));
+  }
+#pragma unroll
+  for (int k = 0; k < CT; ++k) {
+    float b[NBF];
+    const float4 *src = reinterpret_cast<const float4 *>(bsrc + k * WB);
+#pragma unroll
+    for (int j = 0; j < NBF / 4; ++j) {
+      const float4 t = src[j];
+      b[4 * j + 0] = t.x;
+      b[4 * j + 1] = t.y;
+      b[4 * j + 2] = t.z;
+      b[4 * j + 3] = t.w;
+    }
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+      for (int j = 0; j < JW; ++j)
+        acc2[pp][j] = __ffma2_rn(a2[k][pp], make_float2(b[2 * pp + j], b[2 * pp + j]), acc2[pp][j]);
+  }
+}
 
 // One channel-complete SSD block in packed fp32 (sm_100 FADD2 / FFMA2 / FMUL2):
 //   acc2[pp][j].x = sum_k (a[k][2pp]   - slab[k][2pp + j])^2     even pixel, dx = 8*blk + j
@@ -138,14 +193,15 @@ __device__ __forceinline__ void unpack_block(const float2 (&acc2)[2][JW], float 
 // completes full[slot].  Every consumer warp walks every row of its tile in order: wait
 // full, compute if the row is inside its own window (row - warp in [0, maxh)), release.
 // No CTA-wide barrier: warps drift apart by up to NSLOT - TH rows, across tile borders too.
-template <class Cfg, int CT, bool EXACT, class Epi>
-__device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGeom &g, float *ring,
-                                          uint64_t *bars, Epi &epi) {
+template <class Cfg, int CT, int MODE, class Epi>
+__device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const CUtensorMap *tmap_nb,
+                                          const SweepGeom &g, float *ring, uint64_t *bars, Epi &epi) {
+  constexpr bool EXACT = MODE == kExact;
   constexpr int kWarps = Cfg::kWarps, kTH = Cfg::kTH;
   const int kNSlot = g.nslot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_total = kTH + g.maxh - 1;
-  const uint32_t slab_bytes = (uint32_t)(g.C * g.WB * sizeof(float));
+  const uint32_t slab_bytes = (uint32_t)((g.C + (MODE == kDot ? 1 : 0)) * g.WB * sizeof(float));
   const int slab_floats = g.slab_floats;
   const int n8 = g.bs.n8;
   const bool wide_tail = g.bs.tail_r == kR;
@@ -153,6 +209,7 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGe
 
   if (threadIdx.x == 0) {
     prefetch_tmap(tmap);
+    if (MODE == kDot) prefetch_tmap(tmap_nb);
     for (int s = 0; s < kNSlot; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kWarps);
@@ -177,6 +234,8 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGe
           if (y0 + j < g.H2) {
             mbar_arrive_expect_tx(&full[slot], slab_bytes);
             tma_load_4d(ring + slot * slab_floats, tmap, &full[slot], xt, y0 + j, 0, n);
+            if (MODE == kDot)
+              tma_load_4d(ring + slot * slab_floats + g.nb_off, tmap_nb, &full[slot], xt, y0 + j, 0, n);
           } else {
             mbar_arrive(&full[slot]);  // row below the frame: only masked pixels read it
           }
@@ -210,6 +269,22 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGe
         a2[k][1] = make_float2(a[2], a[3]);
       }
     }
+    float2 na2[2];
+    if (MODE == kDot) {
+      // |a|^2 with the same FMA chain the norm pre-pass uses for |b|^2, then a <- -2a (exact)
+      float na[kP] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        na[0] = fmaf(a2[k][0].x, a2[k][0].x, na[0]);
+        na[1] = fmaf(a2[k][0].y, a2[k][0].y, na[1]);
+        na[2] = fmaf(a2[k][1].x, a2[k][1].x, na[2]);
+        na[3] = fmaf(a2[k][1].y, a2[k][1].y, na[3]);
+        a2[k][0] = make_float2(-2.0f * a2[k][0].x, -2.0f * a2[k][0].y);
+        a2[k][1] = make_float2(-2.0f * a2[k][1].x, -2.0f * a2[k][1].y);
+      }
+      na2[0] = make_float2(na[0], na[1]);
+      na2[1] = make_float2(na[2], na[3]);
+    }
     epi.tile_begin(n, y, x0);
 
 #pragma unroll 1
@@ -224,14 +299,20 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGe
 #pragma unroll 1
         for (int blk = 0; blk < nwide; ++blk) {
           float2 acc2[2][kR];
-          ssd_block2<CT, EXACT, kR>(a2, brow + blk * kR, g.WB, acc2);
+          if constexpr (MODE == kDot)
+            dot_block2<CT, kR>(a2, na2, brow + blk * kR, brow + g.nb_off + blk * kR, g.WB, acc2);
+          else
+            ssd_block2<CT, EXACT, kR>(a2, brow + blk * kR, g.WB, acc2);
           float acc[kP][kR];
           unpack_block<kR>(acc2, acc);
           epi.template block<kR>(acc, dy, blk);
         }
         if (!wide_tail) {
           float2 acc2[2][2];
-          ssd_block2<CT, EXACT, 2>(a2, brow + n8 * kR, g.WB, acc2);
+          if constexpr (MODE == kDot)
+            dot_block2<CT, 2>(a2, na2, brow + n8 * kR, brow + g.nb_off + n8 * kR, g.WB, acc2);
+          else
+            ssd_block2<CT, EXACT, 2>(a2, brow + n8 * kR, g.WB, acc2);
           float acc[kP][2];
           unpack_block<2>(acc2, acc);
           epi.template block<2>(acc, dy, n8);
@@ -240,6 +321,7 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const SweepGe
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[slot]);  // this warp is done with the row
     }
+    if constexpr (MODE == kDot) epi.template tile_rescore<CT>(a2, n, y, x0);  // a2 = -2a here
     epi.tile_end(n, y, x0);
     g0 += (uint32_t)rows_total;
   }

@@ -13,7 +13,7 @@ SO_PATH = os.path.join(PKG, "csrc", "libdepthmatch.so")
 
 DM_OK, DM_ERR_INVALID, DM_ERR_CUDA, DM_ERR_UNSUPPORTED, DM_ERR_NOMEM = 0, -1, -2, -3, -4
 DM_VOLUME_SSD, DM_VOLUME_NEG_SOFTMAX, DM_VOLUME_EXACT = 0, 1, 0x100
-DM_FLAG_TIE_MIDDLE, DM_FLAG_EXACT_SSD, DM_FLAG_ASYNC = 1, 2, 4
+DM_FLAG_TIE_MIDDLE, DM_FLAG_EXACT_SSD, DM_FLAG_ASYNC, DM_FLAG_DIFF_SSD = 1, 2, 4, 8
 
 
 class DepthMatchError(RuntimeError):

@@ -11,7 +11,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import (DM_FLAG_ASYNC, DM_FLAG_EXACT_SSD, DM_FLAG_TIE_MIDDLE, DM_VOLUME_EXACT, DM_VOLUME_NEG_SOFTMAX,
+from ._lib import (DM_FLAG_ASYNC, DM_FLAG_DIFF_SSD, DM_FLAG_EXACT_SSD, DM_FLAG_TIE_MIDDLE, DM_VOLUME_EXACT, DM_VOLUME_NEG_SOFTMAX,
                    DM_VOLUME_SSD, DepthMatchError, check, dm_extract_out, dm_pair)
 
 __all__ = [
@@ -200,7 +200,7 @@ def match_volume(in1, in2, maxh, maxw, softmax=False, exact=False, ctx=None):
 
 def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_threshold=0.11,
                   canvas=None, want=("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx"),
-                  ctx=None, out=None, async_=False):
+                  ctx=None, out=None, async_=False, diff_form=False):
     """Fused prepareInput-less forward + processOutput.  Returns a dict of arrays, each
     [N,]H1,W1 (soft_yx: [N,]2,H1,W1; flow_full: [N,]2,hImg,wImg when canvas=(hImg,wImg)).
     `out` may hold preallocated result buffers by name (e.g. pinned host memory), with the
@@ -238,6 +238,8 @@ def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_thres
         setattr(o, name, ptr)
         res[name] = arr
     flags = (DM_FLAG_TIE_MIDDLE if tie_middle else 0) | (DM_FLAG_EXACT_SSD if exact else 0)
+    if diff_form:
+        flags |= DM_FLAG_DIFF_SSD
     if async_:
         if out is None or any(n not in out for n in want) or not _caller_owned_host(in1, a, in2, b):
             raise DepthMatchError(_lib.DM_ERR_INVALID, "async_ needs caller-owned `out` buffers for every "

@@ -80,7 +80,7 @@ int dm_filter_forward(dm_ctx *ctx, const dm_filter *filter, const float *in, int
 local M = {}
 M.C = ffi.load(os.getenv('DEPTHMATCH_SO') or 'depthmatch')
 M.DM_VOLUME_SSD, M.DM_VOLUME_NEG_SOFTMAX = 0, 1
-M.DM_FLAG_TIE_MIDDLE, M.DM_FLAG_EXACT_SSD, M.DM_FLAG_ASYNC = 1, 2, 4
+M.DM_FLAG_TIE_MIDDLE, M.DM_FLAG_EXACT_SSD, M.DM_FLAG_ASYNC, M.DM_FLAG_DIFF_SSD = 1, 2, 4, 8
 
 function M.check(status)
    if status ~= 0 then

@@ -99,6 +99,10 @@ int dm_match_volume(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, int mode
 /* ---- K1+K2 fused: match + extract, volume never written ------------------ */
 #define DM_FLAG_TIE_MIDDLE 1u  /* zero-flow tie rule, opticalflow_model.lua:157-159 */
 #define DM_FLAG_EXACT_SSD 2u   /* unfused mul+add (bit-exact with the CPU path) instead of FMA */
+#define DM_FLAG_DIFF_SSD 8u    /* always form the SSD as sum (a-b)^2.  Default: |a|^2+|b|^2-2a.b (half the
+                                  FP32 work, absolute error a few ulp of |a|^2+|b|^2) whenever the
+                                  largest norms keep that error under the parity bar, decided on
+                                  the device per call; min_ssd is always re-scored as a difference */
 #define DM_FLAG_ASYNC 4u       /* host-buffer call: return once the copies and kernels are queued;
                                   inputs and outputs belong to the library until dm_synchronize(ctx).
                                   Page-locked buffers (dm_host_alloc) make the copies overlap. */
