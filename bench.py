@@ -353,9 +353,12 @@ def main():
                      "note": "fused mode never writes the volume: compulsory traffic is tiny and the "
                              "binding roof is the FP32 pipe, see alu"},
         "alu": {"achieved": ALU_SLOTS * B / (k_ms / 1e3) / 1e12, "unit": "T issue-slots/s (FSUB+FFMA per "
-                "channel per window entry)", "peak": alu_peak / 1e12,
+                "channel per window entry: the algorithmic count of SURVEY 8d)", "peak": alu_peak / 1e12,
                 "frac": ALU_SLOTS * B / (k_ms / 1e3) / alu_peak,
-                "frac_at_observed_clock": ALU_SLOTS * B / (k_ms / 1e3) / (148 * 128 * sm_mhz * 1e6)},
+                "frac_at_observed_clock": ALU_SLOTS * B / (k_ms / 1e3) / (148 * 128 * sm_mhz * 1e6),
+                "ssd_form": os.environ.get("DM_SSD_FORM", "auto (dot: |a|^2+|b|^2-2ab, one FFMA per term; "
+                                           "the kernel executes half the algorithmic slots)"),
+                "kernel_ms_covers": "norm pre-pass + sweep (both twin launches)"},
         "e2e": {"value": e2e_val, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),

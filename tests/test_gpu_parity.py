@@ -736,3 +736,44 @@ def test_async_host_call_and_cropped_view_equal_the_synchronous_call(dm):
     with pytest.raises(dm.DepthMatchError):      # a conversion copy would not outlive the call
         dm.match_extract(in1.astype(np.float64), f2, mh, mh, want=want, ctx=ctx, out=out, async_=True)
     assert ctx.launch_count() > 0
+
+
+def test_dot_and_difference_forms_of_the_ssd_agree(dm, oracle):
+    """The default sweep forms the SSD as |a|^2+|b|^2-2a.b when the norms allow it
+    (DM_FLAG_DIFF_SSD forces sum (a-b)^2).  Both must satisfy the parity bars against the
+    oracle; min_ssd is re-scored in the difference form; large norms fall back on the device."""
+    maxh, maxw = 9, 11
+    in1, in2, _ = make_pair(10, 60, 90, maxh, maxw, seed=31, noise=0.3)
+    K = maxh * maxw
+    want = ("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx")
+    dot = dm.match_extract(in1, in2, maxh, maxw, want=want)
+    dif = dm.match_extract(in1, in2, maxh, maxw, want=want, diff_form=True)
+    vol = oracle.spatial_matching(in1, in2, maxh, maxw)
+    prob = oracle.neg_softmax(vol)
+    idx, pmax = oracle.argmax_tie(prob, K, dm.getMiddleIndex(dm.Geometry(maxh=maxh, maxw=maxw)))
+    gap = oracle.top2_relgap(prob, K)
+    for got in (dot, dif):
+        bad = (got["index"].reshape(-1) != idx) & (gap >= 1e-5)
+        assert bad.sum() == 0
+        np.testing.assert_allclose(got["pmax"].reshape(-1), pmax, rtol=1e-4)
+        np.testing.assert_allclose(got["min_ssd"].reshape(-1), vol.reshape(-1, K).min(-1), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(dot["soft_yx"], dif["soft_yx"], rtol=1e-4)
+    same = dot["index"] == dif["index"]
+    assert same.mean() > 0.999
+    # an exact copy: the dot form would read ~1e-6 where the SSD is exactly 0
+    f2 = in2.copy()
+    f1 = np.ascontiguousarray(f2[:, 3:3 + in1.shape[1], 5:5 + in1.shape[2]])
+    got = dm.match_extract(f1, f2, maxh, maxw, want=("index", "min_ssd"))
+    assert (got["min_ssd"] == 0).all() and (got["index"] == 3 * maxw + 5 + 1).all()
+    # flat frames: every displacement ties bit for bit, the zero-flow rule picks the middle
+    flat1 = np.full((10, 40, 50), 0.7, np.float32)
+    flat2 = np.full((10, 40 + maxh - 1, 50 + maxw - 1), 0.7, np.float32)
+    got = dm.match_extract(flat1, flat2, maxh, maxw, want=("index", "pmax"))
+    assert (got["index"] == dm.getMiddleIndex(dm.Geometry(maxh=maxh, maxw=maxw))).all()
+    np.testing.assert_allclose(got["pmax"], 1.0 / K, rtol=1e-5)
+    # norms beyond the bound: the device-side switch runs the difference kernel, bit for bit
+    big1, big2 = in1 * 30, in2 * 30
+    a = dm.match_extract(big1, big2, maxh, maxw, want=("index", "min_ssd", "pmax"))
+    b = dm.match_extract(big1, big2, maxh, maxw, want=("index", "min_ssd", "pmax"), diff_form=True)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
