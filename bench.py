@@ -202,6 +202,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference)")
     torch.cuda.set_device(local)
+    from depthmatch import parallel as dm_parallel
+    numa_node = None if os.environ.get("DM_NO_NUMA_BIND") else dm_parallel.bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -363,6 +365,7 @@ def main():
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "host": {"numa_node_bound": numa_node, "cpus": len(os.sched_getaffinity(0))},
     }
 
     if not args.no_volume:

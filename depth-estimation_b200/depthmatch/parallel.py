@@ -13,6 +13,8 @@ collective:
 
 One process per GPU; `torch.distributed` is plumbing only.
 """
+import os
+
 import numpy as np
 
 
@@ -68,3 +70,37 @@ def match_extract_row_bands(dm, in1, in2, maxh, maxw, rank, world_size, dist=Non
     out = dm.match_extract(a, b, maxh, maxw, **kw)
     return {k: gather_bands(v, bands, dist, dim=v.dim() - 2) for k, v in out.items()
             if k not in ("n_untouched", "flow_full")}
+
+
+def _parse_cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device=0):
+    """One process per GPU: run this process (and so the first-touch placement of the pinned
+    staging buffers it allocates afterwards) on the CPUs of the NUMA node the GPU's PCIe root
+    hangs off.  With several ranks streaming host buffers at PCIe rate, remote-node buffers
+    halve the aggregate.  Returns the node, or None when the topology is not exposed."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        return None
