@@ -145,23 +145,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// same, for a thread that expects to wait long (the TMA producer): back off between polls so
-// the spin does not steal issue slots from the math warps
+// same, for a thread that expects to wait long (the TMA producer): let the hardware suspend
+// the thread until the phase completes (try_wait's suspend-time hint) instead of polling, so
+// the wait costs the producer's scheduler almost no issue slots
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(256);
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITB_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONEB_%=;\n\t"
+      "bra WAITB_%=;\n\t"
+      "DONEB_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(20000u)
+      : "memory");
 }
 // 4-D tiled TMA load global -> shared, completion on an mbarrier
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,

@@ -120,6 +120,35 @@ __global__ void warp_kernel(int mode, C2P c2p, P2C p2c, const float *field, cons
   }
 }
 
+// sfm2.removeEgoMotion(im, K, R) (out-of-tree sfm2; call sites depth_estimation_api.lua:147,
+// radial/test_radial_opticalflow.lua:192): the previous frame (or its feature maps) seen through
+// the rotated camera, i.e. a homography gather.  Destination pixel (x, y) samples the source at
+// Hm * (x, y, 1) (double arithmetic, one division), bilinear like image.warp; pixels whose
+// source falls outside the frame read 0 and clear the mask.
+struct Homography {
+  double m[9];
+};
+__global__ void homography_kernel(Homography Hm, const float *src, int C, int hs, int ws, int hd, int wd,
+                                  float *dst, float *mask) {
+  const long long plane = (long long)hd * wd;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < plane;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(t / wd), x = (int)(t % wd);
+    const double X = Hm.m[0] * x + Hm.m[1] * y + Hm.m[2];
+    const double Y = Hm.m[3] * x + Hm.m[4] * y + Hm.m[5];
+    const double Z = Hm.m[6] * x + Hm.m[7] * y + Hm.m[8];
+    const float ix = (float)(X / Z), iy = (float)(Y / Z);
+    const bool inside = Z > 0.0 && ix >= 0.0f && ix <= (float)(ws - 1) && iy >= 0.0f && iy <= (float)(hs - 1);
+    long long o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+    float wnw = 0.0f, wne = 0.0f, wsw = 0.0f, wse = 0.0f;
+    if (inside) bilinear_setup(iy, ix, hs, ws, &o00, &o01, &o10, &o11, &wnw, &wne, &wsw, &wse);
+    for (int k = 0; k < C; ++k)
+      dst[(long long)k * plane + t] =
+          inside ? bilinear_tap(src + (long long)k * hs * ws, o00, o01, o10, o11, wnw, wne, wsw, wse) : 0.0f;
+    if (mask) mask[t] = inside ? 1.0f : 0.0f;
+  }
+}
+
 // radial/radial_opticalflow_display.lua:28-53
 __global__ void flow2depth_kernel(const float *flow, int h, int w, float xc, float yc, float infty,
                                   float *depth, float *confs) {
@@ -261,6 +290,28 @@ int dm_warp_bilinear(dm_ctx *ctx, const float *src, int c, int hs, int ws, const
   memset(&a, 0, sizeof(a));
   memset(&b, 0, sizeof(b));
   return warp_common(ctx, 2, a, b, field, src, c, hs, ws, hd, wd, dst);
+}
+
+int dm_warp_homography(dm_ctx *ctx, const float *src, int c, int hs, int ws, const double *hmat, int hd,
+                       int wd, float *dst, float *mask) {
+  DM_REQUIRE(ctx && src && hmat && dst, "dm_warp_homography: NULL argument");
+  DM_REQUIRE(c >= 1 && hs >= 1 && ws >= 1 && hd >= 1 && wd >= 1, "dm_warp_homography: bad shape");
+  DM_CUDA(cudaSetDevice(ctx->device));
+  Call call(ctx);
+  const void *ds;
+  void *dd, *dmask = nullptr;
+  DM_CHECK(call.in(src, (size_t)c * hs * ws * 4, &ds));
+  DM_CHECK(call.out(dst, (size_t)c * hd * wd * 4, &dd));
+  if (mask) DM_CHECK(call.out(mask, (size_t)hd * wd * 4, &dmask));
+  Homography Hm;
+  for (int i = 0; i < 9; ++i) Hm.m[i] = hmat[i];  // host pointer: 9 doubles, read now
+  const long long plane = (long long)hd * wd;
+  int blocks = (int)((plane + 255) / 256);
+  if (blocks > ctx->num_sms * 16) blocks = ctx->num_sms * 16;
+  homography_kernel<<<blocks, 256, 0, ctx->stream>>>(Hm, static_cast<const float *>(ds), c, hs, ws, hd, wd,
+                                                     static_cast<float *>(dd), static_cast<float *>(dmask));
+  count_launch(ctx);
+  return call.finish();
 }
 
 int dm_flow2depth(dm_ctx *ctx, const float *flow, int h, int w, float xcenter, float ycenter,

@@ -20,3 +20,4 @@ from .api import *  # noqa: F401,F403
 from . import torch7io  # noqa: F401
 from .model_io import (loadCalibration, loadModel, loadTesterNetwork, loadWeightsFrom,  # noqa: F401
                        modelDirectory, saveModel, saveNetwork)
+from .depth_estimation_api import DepthEstimationAPI, removeEgoMotion, warpHomography  # noqa: F401

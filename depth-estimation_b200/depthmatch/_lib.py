@@ -80,6 +80,7 @@ SIGNATURES = {
     "dm_c2p_mask": (_I, [_P, _I, _I, _D, _D, _I, _I, _D, _D, _P]),
     "dm_p2c_mask": (_I, [_P, _I, _I, _I, _I, _D, _D, _D, _D, _P]),
     "dm_flow2depth": (_I, [_P, _P, _I, _I, _F, _F, _F, _P, _P]),
+    "dm_warp_homography": (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_double), _I, _I, _P, _P]),
     "dm_post_process_image": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "dm_enlarge_mask": (_I, [_P, _P, _I, _I, _I, _I]),
     "dm_radial_depth": (_I, [_P, _P, _I, _I, _F, _F, _F, _P, _P]),

@@ -53,6 +53,8 @@ int dm_warp_bilinear(dm_ctx *ctx, const float *src, int c, int hs, int ws, const
                      int hd, int wd, float *dst);
 int dm_flow2depth(dm_ctx *ctx, const float *flow, int h, int w, float xcenter, float ycenter,
                   float infty, float *depth, float *confs);
+int dm_warp_homography(dm_ctx *ctx, const float *src, int c, int hs, int ws, const double *hmat,
+                       int hd, int wd, float *dst, float *mask);
 int dm_post_process_image(dm_ctx *ctx, const float *input, const float *mask, int h, int w,
                           int winsize, int method_max, float *output);
 int dm_enlarge_mask(dm_ctx *ctx, float *mask, int h, int w, int ix, int iy);

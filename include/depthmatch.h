@@ -215,6 +215,13 @@ int dm_radial_depth(dm_ctx *ctx, const float *flow, int h, int w, float mh, floa
 int dm_depth_from_xflow(dm_ctx *ctx, const float *xflow, const float *mask, int h, int w, float m,
                         float *depth, float *conf);
 
+/* sfm2.removeEgoMotion(im, K, R) (out-of-tree sfm2; depth_estimation_api.lua:147,
+ * radial/test_radial_opticalflow.lua:192): homography gather.  dst[k][y][x] = bilinear sample of
+ * src[k] at hmat * (x, y, 1) (hmat: 9 doubles row-major, HOST pointer, e.g. K * R * K^-1);
+ * outside the source frame dst = 0 and mask (optional, [hd][wd]) = 0, else mask = 1. */
+int dm_warp_homography(dm_ctx *ctx, const float *src, int c, int hs, int ws, const double *hmat,
+                       int hd, int wd, float *dst, float *mask);
+
 /* ---- next row 3: the feature extractor in front of the path ---------------------- */
 /* One layer of getFilter (opticalflow_model.lua:45-79; radial/radial_opticalflow_network.lua:6-31).
  * n_conn == 0: nn.SpatialConvolution(n_in, n_out, kw, kh), weight [n_out][n_in][kh][kw].

@@ -160,6 +160,11 @@ double orc_get_rmax(int h, int w, double ex, double ey);
 void orc_warp_bilinear(const float *src, int C, int hs, int ws, const float *field, int hd,
                        int wd, float *dst);
 
+/* sfm2.removeEgoMotion as a homography gather (out-of-tree sfm2; depth_estimation_api.lua:147):
+ * dst(x,y) = bilinear src(hmat*(x,y,1)); outside: 0, mask 0.  PARITY UNPINNED. */
+void orc_warp_homography(const float *src, int C, int hs, int ws, const double *hmat, int hd, int wd,
+                         float *dst, float *mask);
+
 /* flow2depth inline C (radial/radial_opticalflow_display.lua:6-58). */
 void orc_flow2depth(const float *flow, int h, int w, float xcenter, float ycenter,
                     float infty, float *depth, float *confs);

@@ -122,3 +122,39 @@ void orc_flow2depth(const float *flow, int h, int w, float xcenter, float ycente
       }
     }
 }
+
+/* sfm2.removeEgoMotion (out-of-tree sfm2; call sites depth_estimation_api.lua:147,
+ * radial/test_radial_opticalflow.lua:192), restated as a homography gather: destination (x, y)
+ * samples the source at hmat * (x, y, 1), bilinear like image.warp; outside the frame 0 and
+ * mask = 0.  PARITY UNPINNED (the library is not in the tree). */
+void orc_warp_homography(const float *src, int C, int hs, int ws, const double *hmat, int hd, int wd,
+                         float *dst, float *mask) {
+  for (int y = 0; y < hd; ++y)
+    for (int x = 0; x < wd; ++x) {
+      const double X = hmat[0] * x + hmat[1] * y + hmat[2];
+      const double Y = hmat[3] * x + hmat[4] * y + hmat[5];
+      const double Z = hmat[6] * x + hmat[7] * y + hmat[8];
+      const float ix = (float)(X / Z), iy = (float)(Y / Z);
+      const int inside = Z > 0.0 && ix >= 0.0f && ix <= (float)(ws - 1) && iy >= 0.0f && iy <= (float)(hs - 1);
+      if (mask) mask[(size_t)y * wd + x] = inside ? 1.0f : 0.0f;
+      if (!inside) {
+        for (int k = 0; k < C; ++k) dst[((size_t)k * hd + y) * wd + x] = 0.0f;
+        continue;
+      }
+      const long x0 = (long)floorf(ix), y0 = (long)floorf(iy);
+      const long x1 = x0 + 1, y1 = y0 + 1;
+      const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
+      const float wne = (ix - (float)x0) * ((float)y1 - iy);
+      const float wsw = ((float)x1 - ix) * (iy - (float)y0);
+      const float wse = (ix - (float)x0) * (iy - (float)y0);
+      const long x1c = x1 < ws - 1 ? x1 : ws - 1, y1c = y1 < hs - 1 ? y1 : hs - 1;
+      for (int k = 0; k < C; ++k) {
+        const float *s = src + (size_t)k * hs * ws;
+        const float a = s[y0 * ws + x0] * wnw;
+        const float b = s[y0 * ws + x1c] * wne;
+        const float c = s[y1c * ws + x0] * wsw;
+        const float d = s[y1c * ws + x1c] * wse;
+        dst[((size_t)k * hd + y) * wd + x] = ((a + b) + c) + d;
+      }
+    }
+}

@@ -423,3 +423,16 @@ def filter_forward(inp, layers, pads=(0, 0, 0, 0)):
         x = conv_layer(x, L["weight"], L["bias"], L.get("conn"), pads if i == 0 else (0, 0, 0, 0),
                        L.get("tanh", False))
     return x
+
+
+def warp_homography(src, hmat, hd=None, wd=None):
+    """removeEgoMotion as a homography gather: returns (warped [C,hd,wd], mask [hd,wd])."""
+    src, ps = _f(src)
+    Cn, hs, ws = src.shape
+    hd, wd = hd or hs, wd or ws
+    hm = np.ascontiguousarray(hmat, np.float64).reshape(9)
+    dst = np.empty((Cn, hd, wd), np.float32)
+    mask = np.empty((hd, wd), np.float32)
+    lib().orc_warp_homography(ps, Cn, hs, ws, hm.ctypes.data_as(C.POINTER(C.c_double)), hd, wd,
+                              dst.ctypes.data_as(c_fp), mask.ctypes.data_as(c_fp))
+    return dst, mask

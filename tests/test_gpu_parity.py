@@ -777,3 +777,61 @@ def test_dot_and_difference_forms_of_the_ssd_agree(dm, oracle):
     b = dm.match_extract(big1, big2, maxh, maxw, want=("index", "min_ssd", "pmax"), diff_form=True)
     for k in a:
         np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_depth_estimation_api_next_frame_depth(dm, oracle):
+    """depth_estimation_api.lua's nextFrameDepth from the scaled frame on: ego-motion warp of the
+    previous features, filter, prepareInput, matching, soft-max, 'mean' extraction, enlargeMask,
+    mask composition -- against the same chain built from the oracle's pieces."""
+    rng = np.random.default_rng(41)
+    hImg, wImg, maxh, maxw = 60, 84, 7, 9
+    g = dm.Geometry(layers=[[3, 5, 5, 6]], maxh=maxh, maxw=maxw, hImg=hImg, wImg=wImg)
+    flt = dm.getFilter(g, rng)
+    layers = _oracle_layers(flt, dm)
+    base = rng.random((3, hImg + 8, wImg + 8)).astype(np.float32)
+    frames = [np.ascontiguousarray(base[:, 4 + s:4 + s + hImg, 4 - s:4 - s + wImg]) for s in (0, 1, 2)]
+    K = np.array([[70.0, 0, wImg], [0, 70.0, hImg], [0, 0, 1]])       # full-size camera; Khalf is used
+    a = 0.01
+    R = np.array([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1]])
+    api = dm.DepthEstimationAPI(g, flt, K=K, first_frame=frames[0])
+    Khalf = K * 0.5
+    Khalf[2, 2] = 1
+    Hm = Khalf @ R @ np.linalg.inv(Khalf)
+    last = oracle.filter_forward(frames[0], layers)
+    for t in (1, 2):
+        im, xflow, mask = api.nextFrameDepth(frames[t], R=R, nFound=100, nInliers=90)
+        # the oracle's chain
+        warped, wmask = oracle.warp_homography(last, Hm)
+        filt = oracle.filter_forward(frames[t], layers)
+        in1, in2 = dm.prepareInput(g, warped, filt)
+        prob = oracle.neg_softmax(oracle.spatial_matching(np.ascontiguousarray(in1), in2, maxh, maxw))
+        ym, xm = oracle.soft_mean(prob, maxh, maxw)
+        h1, w1 = in1.shape[1:]
+        pm = oracle.marginal_x(prob, maxh, maxw).reshape(h1, w1, maxh)
+        _, sc, _ = oracle.extract_output(pm, 0.11, np.zeros((h1, w1), np.int64), np.zeros((h1, w1), np.float32))
+        conf = np.zeros((hImg, wImg), np.float32)
+        hoff, woff = (hImg - h1) // 2, (wImg - w1) // 2
+        conf[hoff:hoff + h1, woff:woff + w1] = sc > 0
+        want_x = np.zeros((hImg, wImg), np.float32)
+        want_x[hoff:hoff + h1, woff:woff + w1] = xm.reshape(h1, w1) - math.ceil(maxw / 2)
+        m = oracle.enlarge_mask(wmask, math.ceil((wImg - w1) / 2), math.ceil((hImg - h1) / 2))
+        mh, mw = m.shape
+        want_mask = np.zeros((hImg, wImg), np.float32)
+        oy, ox = (hImg - mh) // 2 - 1, (wImg - mw) // 2 - 1
+        want_mask[oy:oy + mh, ox:ox + mw] = m
+        want_mask *= conf
+        assert xflow.shape == (hImg, wImg) and mask.shape == (hImg, wImg)
+        np.testing.assert_allclose(xflow, want_x, rtol=0, atol=2e-3)
+        assert (mask != want_mask).mean() < 2e-3
+        assert 0.05 < mask.mean() < 1.0
+        last = filt
+    # a bad frame (few inliers): zero flow, zero mask, the state still advances
+    _, xflow, mask = api.nextFrameDepth(frames[0], R=R, nFound=100, nInliers=5)
+    assert not xflow.any() and not mask.any()
+    # the homography warp alone, against the oracle (identity and a rotation)
+    src = rng.random((4, 30, 44)).astype(np.float32)
+    for Hq in (np.eye(3), Hm, np.array([[1, 0, 2.5], [0, 1, -1.25], [0, 0, 1.0]])):
+        want, wm = oracle.warp_homography(src, Hq)
+        got, gm = dm.warpHomography(src, Hq)
+        np.testing.assert_array_equal(gm, wm)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
