@@ -158,7 +158,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
       "bra WAITB_%=;\n\t"
       "DONEB_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(20000u)
+      "r"(parity), "r"(1000u)
       : "memory");
 }
 // 4-D tiled TMA load global -> shared, completion on an mbarrier

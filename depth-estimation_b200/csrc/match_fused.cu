@@ -59,7 +59,7 @@ struct ExtractParams {
 // minimum (and its index), the softmax denominator and -- when SOFT -- the two first
 // moments, all relative to the running minimum (flash-style rescaling when it moves).
 // Shared memory per pixel: the shortlist bitmap [nwords] and the SSD of the zero-flow entry.
-template <bool SOFT>
+template <bool SOFT, bool DOT>
 struct ExtractEpi {
   static constexpr int kCThreads = ExtractCfg::kCThreads;
   const ExtractParams &P;
@@ -72,8 +72,6 @@ struct ExtractEpi {
   int vfrom[kP];
   unsigned *mask;  // [nwords][kP][kCThreads] words, this thread's column
   float *vmid;     // [kP][kCThreads]
-  float mexact[kP];  // kDot: the winner's SSD re-scored in the difference form
-  bool rescored = false;
 
   __device__ ExtractEpi(const ExtractParams &p, unsigned *smem_extra)
       : P(p), mask(smem_extra + threadIdx.x) {
@@ -207,11 +205,9 @@ struct ExtractEpi {
   // would read a few ulp of |a|^2 + |b|^2 instead of 0).  a2 holds -2a.
   template <int CT>
   __device__ __forceinline__ void tile_rescore(const float2 (&a2)[CT][2], int n, int y, int x0) {
-    rescored = true;
-    if (!P.min_ssd || y >= P.g.H1) return;
+    if (!DOT || !P.min_ssd || y >= P.g.H1) return;
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
-      mexact[p] = 0.0f;
       if (x0 + p >= P.g.W1) continue;
       const int dy = (idx[p] - 1) / P.g.maxw, dx = (idx[p] - 1) % P.g.maxw;
       const float *b = P.in2 + (long long)n * P.s2n + (long long)(y + dy) * P.s2y + (x0 + p + dx);
@@ -223,7 +219,7 @@ struct ExtractEpi {
         const float d = a - (k < P.g.Cin ? __ldg(b + (long long)k * P.s2c) : 0.0f);
         acc = fmaf(d, d, acc);
       }
-      mexact[p] = acc;
+      P.min_ssd[((size_t)n * P.g.H1 + y) * P.g.W1 + x0 + p] = acc;
     }
   }
 
@@ -243,7 +239,7 @@ struct ExtractEpi {
         if (emid * inv == inv) win = P.middle;  // p[middle] == max p (opticalflow_model.lua:157-159)
       }
       if (P.index) P.index[o] = win;
-      if (P.min_ssd) P.min_ssd[o] = rescored ? mexact[p] : m[p];
+      if (P.min_ssd && !DOT) P.min_ssd[o] = m[p];  // kDot: written by tile_rescore
       if (P.pmax) P.pmax[o] = inv;
       if (SOFT && P.soft_yx) {
         const size_t plane = (size_t)g.H1 * g.W1;
@@ -304,7 +300,7 @@ match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   float *ring = reinterpret_cast<float *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)P.g.nslot * P.g.slab_floats);
   unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
-  ExtractEpi<SOFT> epi(P, extra);
+  ExtractEpi<SOFT, MODE == kDot> epi(P, extra);
   run_sweep<ExtractCfg, CT, MODE>(&tmap, &tmap_nb, P.g, ring, full, epi);
 }
 
@@ -912,7 +908,10 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   // ~1e-5 (the parity bar on the soft-max scores): a pre-pass writes |b|^2 per frame-2 pixel and
   // the maxima, then both kernels are launched and the device-side bound lets one of them run.
   const char *force = getenv("DM_SSD_FORM");  // "diff" / "dot": tuning and tests only
-  const bool allow_dot = !exact && !(flags & DM_FLAG_DIFF_SSD) && !(force && !strcmp(force, "diff"));
+  // small calls (one 320x180 pair with a 17x17 window) are launch-bound: the pre-pass and the
+  // twin launch would cost more than the dot form saves
+  const bool big = (double)npx * maxh * maxw * pr.Cin >= 5.0e8 || (force && !strcmp(force, "dot"));
+  const bool allow_dot = big && !exact && !(flags & DM_FLAG_DIFF_SSD) && !(force && !strcmp(force, "diff"));
   bool twin = false;
   ExtractParams Pd = P;
   CUtensorMap nbmap;

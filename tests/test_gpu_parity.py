@@ -738,10 +738,12 @@ def test_async_host_call_and_cropped_view_equal_the_synchronous_call(dm):
     assert ctx.launch_count() > 0
 
 
-def test_dot_and_difference_forms_of_the_ssd_agree(dm, oracle):
-    """The default sweep forms the SSD as |a|^2+|b|^2-2a.b when the norms allow it
-    (DM_FLAG_DIFF_SSD forces sum (a-b)^2).  Both must satisfy the parity bars against the
-    oracle; min_ssd is re-scored in the difference form; large norms fall back on the device."""
+def test_dot_and_difference_forms_of_the_ssd_agree(dm, oracle, monkeypatch):
+    """Large calls form the SSD as |a|^2+|b|^2-2a.b when the norms allow it (DM_FLAG_DIFF_SSD
+    forces sum (a-b)^2).  Both must satisfy the parity bars against the oracle; min_ssd is
+    re-scored in the difference form; large norms fall back on the device.  DM_SSD_FORM=dot
+    forces the dot kernel on inputs small enough for the oracle."""
+    monkeypatch.setenv("DM_SSD_FORM", "dot")
     maxh, maxw = 9, 11
     in1, in2, _ = make_pair(10, 60, 90, maxh, maxw, seed=31, noise=0.3)
     K = maxh * maxw
@@ -771,10 +773,18 @@ def test_dot_and_difference_forms_of_the_ssd_agree(dm, oracle):
     got = dm.match_extract(flat1, flat2, maxh, maxw, want=("index", "pmax"))
     assert (got["index"] == dm.getMiddleIndex(dm.Geometry(maxh=maxh, maxw=maxw))).all()
     np.testing.assert_allclose(got["pmax"], 1.0 / K, rtol=1e-5)
-    # norms beyond the bound: the device-side switch runs the difference kernel, bit for bit
+    # automatic mode on a call large enough for the dot form: unit-variance features take it
+    # (results differ from the difference form in the last bits), norms beyond the bound make the
+    # device-side switch run the difference kernel, bit for bit
+    monkeypatch.delenv("DM_SSD_FORM")
+    in1, in2, _ = make_pair(10, 260, 260, 33, 33, seed=32, noise=0.2)
+    a = dm.match_extract(in1, in2, 33, 33, want=("index", "pmax"))
+    b = dm.match_extract(in1, in2, 33, 33, want=("index", "pmax"), diff_form=True)
+    assert (a["index"] == b["index"]).mean() > 0.999 and not np.array_equal(a["pmax"], b["pmax"])
+    np.testing.assert_allclose(a["pmax"], b["pmax"], rtol=1e-4)
     big1, big2 = in1 * 30, in2 * 30
-    a = dm.match_extract(big1, big2, maxh, maxw, want=("index", "min_ssd", "pmax"))
-    b = dm.match_extract(big1, big2, maxh, maxw, want=("index", "min_ssd", "pmax"), diff_form=True)
+    a = dm.match_extract(big1, big2, 33, 33, want=("index", "min_ssd", "pmax"))
+    b = dm.match_extract(big1, big2, 33, 33, want=("index", "min_ssd", "pmax"), diff_form=True)
     for k in a:
         np.testing.assert_array_equal(a[k], b[k])
 
