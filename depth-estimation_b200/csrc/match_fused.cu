@@ -160,28 +160,38 @@ struct ExtractEpi {
     const float rowf = (float)(dy + 1);
     bool cand = false;
     float eb[kP], ebm[kP];
+    // soft-max terms two pixels at a time: acc[2pp][r] and acc[2pp+1][r] are the halves of one
+    // packed accumulator, so the scale and the sums are FFMA2 / FADD2 (same roundings as scalar)
 #pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      const float mL = m[p] * kLog2e;
-      float ex = 0.0f;
-      eb[p] = 0.0f;
+    for (int pp = 0; pp < kP / 2; ++pp) {
+      const float2 mL2 = make_float2(m[2 * pp] * kLog2e, m[2 * pp + 1] * kLog2e);
+      float2 eb2 = make_float2(0.0f, 0.0f), ex2 = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float e = ex2_approx(fmaf(acc[p][r], -kLog2e, mL));
-        eb[p] += e;
-        if (SOFT) ex = fmaf(e, (float)(r + 1), ex);
+        const float2 t = __ffma2_rn(make_float2(acc[2 * pp][r], acc[2 * pp + 1][r]),
+                                    make_float2(-kLog2e, -kLog2e), mL2);
+        const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        eb2 = __fadd2_rn(eb2, e);
+        if (SOFT) ex2 = __ffma2_rn(e, make_float2((float)(r + 1), (float)(r + 1)), ex2);
       }
-      S[p] += eb[p];
-      if (SOFT) {
-        sx[p] += fmaf(eb[p], (float)(dx0 - (p & 1)), ex);  // column = dx + 1
-        sy[p] = fmaf(eb[p], rowf, sy[p]);
-      }
-      // thresholded extraction: p_k(final) <= e_k / S(now), so an entry of this block can
-      // end above the threshold only if the block's largest e exceeds thr * S
-      ebm[p] = 0.0f;
-      if (P.nwords) {
-        ebm[p] = ex2_approx(fmaf(bm[p], -kLog2e, mL));
-        cand |= ebm[p] > P.thr_lo * S[p];
+      eb[2 * pp] = eb2.x;
+      eb[2 * pp + 1] = eb2.y;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p = 2 * pp + h;
+        const float ex = h ? ex2.y : ex2.x;
+        S[p] += eb[p];
+        if (SOFT) {
+          sx[p] += fmaf(eb[p], (float)(dx0 - (p & 1)), ex);  // column = dx + 1
+          sy[p] = fmaf(eb[p], rowf, sy[p]);
+        }
+        // thresholded extraction: p_k(final) <= e_k / S(now), so an entry of this block can
+        // end above the threshold only if the block's largest e exceeds thr * S
+        ebm[p] = 0.0f;
+        if (P.nwords) {
+          ebm[p] = ex2_approx(fmaf(bm[p], -kLog2e, h ? mL2.y : mL2.x));
+          cand |= ebm[p] > P.thr_lo * S[p];
+        }
       }
     }
     if (cand) {
