@@ -21,3 +21,4 @@ from . import torch7io  # noqa: F401
 from .model_io import (loadCalibration, loadModel, loadTesterNetwork, loadWeightsFrom,  # noqa: F401
                        modelDirectory, saveModel, saveNetwork)
 from .depth_estimation_api import DepthEstimationAPI, removeEgoMotion, warpHomography  # noqa: F401
+from .radial_api import RadialTester, polarGeometry  # noqa: F401

@@ -22,7 +22,7 @@ __all__ = [
     "getRMax", "getC2PMask", "getP2CMask", "cartesian2polar", "polar2cartesian", "getKOutput",
     "getP2CMaskOF", "flow2depth", "match_extract", "match_volume", "round_lua",
     "postProcessImage", "enlargeMask", "radial", "computeDepthMapFromFlow",
-    "Filter", "getFilter", "getRadialFilter", "getMultiscalePrefilter", "downsample",
+    "Filter", "getFilter", "getRadialFilter", "getMultiscalePrefilter", "downsample", "multiscaleInputs",
 ]
 
 try:  # torch is plumbing only (device memory + streams); the package works without it
@@ -652,6 +652,24 @@ def getMultiscalePrefilter(geometry, filter, ctx=None):
 
     prefilter.getWeights = filter.getWeights
     return prefilter
+
+
+def multiscaleInputs(geometry, filter, img1, img2, ctx=None):
+    """The per-scale {f1, f2} pairs getModelMultiscale(prefiltered) takes, from two raw frames:
+    every scale is the r x r average of the frame, zero-padded by the filter footprint
+    (getMultiscalePrefilter) -- frame 2 by the search window on top, so that f2 is
+    (maxh-1, maxw-1) larger than f1 and every displacement of the window is a valid read --
+    and run through the shared filter."""
+    wPad, hPad = geometry.wPatch2 - 1, geometry.hPatch2 - 1
+    p1 = (wPad // 2, wPad - wPad // 2, hPad // 2, hPad - hPad // 2)
+    wl, wt = (geometry.maxw - 1) // 2, (geometry.maxh - 1) // 2
+    p2 = (p1[0] + wl, p1[1] + geometry.maxw - 1 - wl, p1[2] + wt, p1[3] + geometry.maxh - 1 - wt)
+    out = []
+    for r in geometry.ratios:
+        a = downsample(img1, r, ctx=ctx) if r != 1 else img1
+        b = downsample(img2, r, ctx=ctx) if r != 1 else img2
+        out.append((filter.forward(a, p1), filter.forward(b, p2)))
+    return out
 
 
 def downsample(img, r, ctx=None):

@@ -53,6 +53,19 @@ def main():
     model = dm.getModelMultiscale(geo, True, True)
     ms = timed(lambda: model.forward(inp))
     res["c3 multiscale 640x360 {1,2,4} 8x8"] = {"ms": ms, "pairs_per_s": 1e3 / ms}
+    # c3 from raw frames: r x r average, zero padding, shared {3,5,5,10} filter per scale, then the model
+    geo3 = dm.Geometry(maxh=8, maxw=8, ratios=[1, 2, 4], multiscale=True, hImg=360, wImg=640, wPatch2=5, hPatch2=5,
+                       layers=[[3, 5, 5, 10]], share_filters=True, output_extraction_method="max")
+    flt3 = dm.getFilter(geo3, np.random.default_rng(3))
+    fr3 = torch.rand((2, 3, 360, 640), device="cuda", generator=g)
+    ms = timed(lambda: model.forward(dm.multiscaleInputs(geo3, flt3, fr3[0], fr3[1])))
+    res["c3 from raw frames: 3 x (average, pad, filter) per frame + multiscale model"] = {"ms": ms, "pairs_per_s": 1e3 / ms}
+    # c4 from raw frames: polar remap of both frames, 1x17 / 17x1 filter, radial matcher, unmap, depth
+    netp = dict(wImg=640, hImg=360, wInput=400, hInput=400, wKernel=17, hKernel=17, hWin=15,
+                layers=[[3, 1, 17, 5], [5, 17, 1, 10]])
+    tester = dm.RadialTester(netp, dm.getRadialFilter(netp, np.random.default_rng(4)))
+    ms = timed(lambda: tester.forward(fr3[0], fr3[1], (320.73, 172.48)))
+    res["c4 from raw frames: polar remap x2, filter x2, radial match, unmap, flow2depth"] = {"ms": ms, "pairs_per_s": 1e3 / ms}
     # c4: polar remap 640x360 -> 400x(400+16), radial matcher hWin 15 on 10x384x400
     img = torch.rand((3, 360, 640), device="cuda", generator=g)
     e2 = (320.73, 172.48)

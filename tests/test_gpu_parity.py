@@ -845,3 +845,74 @@ def test_depth_estimation_api_next_frame_depth(dm, oracle):
         got, gm = dm.warpHomography(src, Hq)
         np.testing.assert_array_equal(gm, wm)
         np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+
+
+def test_radial_pipeline_from_frames_vs_oracle_chain(dm, oracle):
+    """Config 4 in small, from RGB frames: polar remap (LUT and analytic), shared 1x17 / 17x1
+    filter, radial matcher + argmin, back to cartesian, flow2depth -- against the oracle's chain.
+    The epipole comes from the reference's gopro.cal (tests/golden/ref_calibration.npz)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_calibration.npz"))
+    cal = dm.torch7io.loads(z["gopro"].tobytes())
+    netp = dict(wImg=160, hImg=90, wInput=96, hInput=100, wKernel=17, hKernel=17, hWin=9,
+                layers=[[3, 1, 17, 5], [5, 17, 1, 10]])
+    e2 = (float(cal.K[0, 2]) * netp["wImg"] / cal.wImg, float(cal.K[1, 2]) * netp["wImg"] / cal.wImg)
+    rng = np.random.default_rng(51)
+    flt = dm.getRadialFilter(netp, rng)
+    layers = _oracle_layers(flt, dm)
+    base = rng.random((3, 90, 160)).astype(np.float32)
+    prev = base
+    img = np.clip(base + 0.02 * rng.standard_normal(base.shape), 0, 1).astype(np.float32)
+    got = dm.RadialTester(netp, flt, use_masks=True).forward(prev, img, e2)
+    # oracle chain (radial/test_radial_opticalflow.lua:183-221)
+    rmax = oracle.get_rmax(90, 160, *e2)
+    m = oracle.c2p_mask(96, 100, e2[0], e2[1], 8, 8, rmax, 1.0)
+    p_img, p_prev = oracle.warp_bilinear(img, m), oracle.warp_bilinear(prev, m)
+    f_prev = oracle.filter_forward(np.ascontiguousarray(p_prev[:, :100 - 9 + 1]), layers)
+    f_img = oracle.filter_forward(p_img, layers)
+    vol = oracle.radial_matching(f_prev, f_img, 9)
+    idx, _ = oracle.argmin_tie(vol, 9, 0)
+    gap = np.sort(vol.reshape(-1, 9), -1)
+    safe = ((gap[:, 1] - gap[:, 0]) > 1e-4 * np.maximum(gap[:, 0], 1e-6)).reshape(f_prev.shape[1:])
+    want_idx = (idx - 1).reshape(f_prev.shape[1:]).astype(np.float32)
+    assert got["polar_flow"].shape == want_idx.shape == (76, 96)
+    assert (got["polar_flow"] != want_idx)[safe].sum() == 0 and safe.mean() > 0.9
+    hPolar = 100 - 17 - 9 + 2
+    k = hPolar / 100
+    m2 = oracle.p2c_mask(96, hPolar, int(160 * k), int(90 * k), e2[0] * k, e2[1] * k, rmax * k, 1.0)
+    cart = oracle.warp_bilinear(got["polar_flow"][None], m2)[0]
+    np.testing.assert_allclose(got["cart_flow"], cart, rtol=0, atol=1e-4)
+    kout = dm.getKOutput(netp)
+    infty = rmax * 0.65
+    d, c = oracle.flow2depth(got["cart_flow"], e2[0] * kout, e2[1] * kout, infty)
+    np.testing.assert_array_equal(got["confs"], c)
+    np.testing.assert_allclose(got["depth"], d / np.float32(infty), rtol=1e-6)
+    # the analytic remaps (no LUT in HBM) agree with the LUT path up to the libm of the device
+    ana = dm.RadialTester(netp, flt, use_masks=False).forward(prev, img, e2)
+    assert (ana["polar_flow"] != got["polar_flow"])[safe].mean() < 0.01
+
+
+def test_multiscale_from_raw_frames(dm, oracle):
+    """Config 3 from frames: multiscaleInputs (average, padding, shared filter per scale) feeds
+    getModelMultiscale; the result equals the oracle's cascade on the same feature maps and a
+    planted shift of the second frame is recovered away from the zero-padded border."""
+    rng = np.random.default_rng(61)
+    g = dm.Geometry(maxh=8, maxw=8, ratios=[1, 2, 4], multiscale=True, hImg=64, wImg=96, wPatch2=5, hPatch2=5,
+                    layers=[[3, 5, 5, 10]], share_filters=True, output_extraction_method="max")
+    flt = dm.getFilter(g, rng)
+    base = rng.random((3, 64 + 16, 96 + 16)).astype(np.float32)
+    img2 = np.ascontiguousarray(base[:, 8:72, 8:104])
+    # frame-2 content at (+4, +4): an integer displacement at every scale (with random filters the
+    # un-normalised cascade only recovers flows all the scales agree on)
+    img1 = np.ascontiguousarray(base[:, 8 + 4:72 + 4, 8 + 4:104 + 4])
+    inp = dm.multiscaleInputs(g, flt, img1, img2)
+    for (f1, f2), r in zip(inp, g.ratios):
+        assert f1.shape == (10, 64 // r, 96 // r) and f2.shape == (10, 64 // r + 7, 96 // r + 7)
+    out = dm.getModelMultiscale(g, True, True).forward(inp)
+    # oracle on the same maps
+    f1s, f2s = [np.asarray(a) for a, _ in inp], [np.asarray(b) for _, b in inp]
+    idx, fy, fx, gap = _multiscale_oracle(oracle, f1s, f2s, 8, 8, g.ratios)
+    tie = gap < NEAR_TIE * 10
+    assert ((np.asarray(out["index"]).reshape(-1) != idx) & ~tie).sum() == 0 and tie.mean() < 0.05
+    inner = (slice(20, 44), slice(24, 72))
+    assert np.median(np.asarray(out["flow_y"])[inner]) == 4 and np.median(np.asarray(out["flow_x"])[inner]) == 4
