@@ -276,6 +276,33 @@ int generic_match_volume(Call &call, const dm_pair *in, int maxh, int maxw, int 
   return launch_generic(call.ctx, P, true);
 }
 
+// nn.SpatialRadialMatching + `output:min(3)` (radial/radial_opticalflow_network.lua:32-34,
+// radial/test_radial_opticalflow.lua:204-207) need no soft-max: one thread per pixel walks the
+// hWin rows below it, every load coalesced along the polar angle; SSD with separately rounded
+// multiply and add like the CPU path, strict < (first occurrence).
+__global__ void radial_argmin_kernel(const GenericParams P) {
+  const long long npx = (long long)P.N * P.H1 * P.W1;
+  for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < npx;
+       px += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(px % P.W1);
+    const int y = (int)((px / P.W1) % P.H1);
+    const int n = (int)(px / ((long long)P.W1 * P.H1));
+    const float *a = P.in1 + n * P.s1n + y * P.s1y + x;
+    const float *b0 = P.in2 + n * P.s2n + y * P.s2y + x;
+    float vbest = __int_as_float(0x7f800000);
+    int dbest = 0;
+    for (int d = 0; d < P.maxh; ++d) {
+      const float v = ssd_at(P, a, b0 + d * P.s2y, true);
+      if (v < vbest) {
+        vbest = v;
+        dbest = d;
+      }
+    }
+    P.radial_flow[px] = (float)dbest;
+    if (P.min_ssd) P.min_ssd[px] = vbest;
+  }
+}
+
 }  // namespace dm
 
 using namespace dm;
@@ -298,6 +325,13 @@ extern "C" int dm_radial_match_extract(dm_ctx *ctx, const dm_pair *in, int h_win
     DM_CHECK(call.out(min_ssd, npx * sizeof(float), &p));
     P.min_ssd = static_cast<float *>(p);
   }
-  DM_CHECK(launch_generic(ctx, P, false));
+  {
+    long long blocks = ((long long)npx + 127) / 128;
+    if (blocks > (long long)ctx->num_sms * 32) blocks = (long long)ctx->num_sms * 32;
+    prof_begin(ctx);
+    radial_argmin_kernel<<<(int)blocks, 128, 0, ctx->stream>>>(P);
+    prof_end(ctx);
+    count_launch(ctx);
+  }
   return call.finish();
 }
