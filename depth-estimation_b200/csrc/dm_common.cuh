@@ -71,6 +71,10 @@ struct dm_ctx {
   // H2D of chunk i+1 overlaps the kernels of chunk i and the D2H of chunk i-1
   dm_ctx *pipe[2] = {nullptr, nullptr};
   bool is_child = false;
+  // side streams for independent sub-problems of one call (the scales of the multiscale model):
+  // forked from and joined to `stream` with events, created on first use
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};
 };
 
 namespace dm {

@@ -232,6 +232,11 @@ int dm_destroy(dm_ctx *ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+    if (ctx->aux_join[i]) cudaEventDestroy(ctx->aux_join[i]);
+  }
+  if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
   delete ctx;
   return DM_OK;
 }

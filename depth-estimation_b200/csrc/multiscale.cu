@@ -243,18 +243,77 @@ ring_argmax_kernel(ScaleMaps maps, const int *chain, int h, int w, int maxh, int
   const int lane = threadIdx.x & 31;
   const int K = maxh * maxw, n = R.n;
   const long long npx = (long long)h * w;
-  for (long long px = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); px < npx;
-       px += (long long)gridDim.x * 8) {
-    const int Y = (int)(px / w), X = (int)(px % w);
-    const float *base[kMaxRatios];
+  // a lane sees the same entries l = lane + 32 e for every pixel: their per-scale offsets live
+  // in registers (L <= 256 and at most three scales, which covers the reference's geometries: L = 112, 160)
+  constexpr int kLaneEntries = 8, kRegRatios = 3;
+  const bool in_regs = L <= 32 * kLaneEntries && n <= kRegRatios;
+  int offs[kLaneEntries][kRegRatios];
+  if (in_regs) {
 #pragma unroll
-    for (int s = 0; s < kMaxRatios; ++s)
-      if (s < n) {
-        const int rs = R.r[s];
-        base[s] = maps.p[s] + ((long long)(Y / rs) * (w / rs) + (X / rs)) * K;
+    for (int e = 0; e < kLaneEntries; ++e)
+#pragma unroll
+      for (int s = 0; s < kRegRatios; ++s) {
+        const int l = lane + 32 * e;
+        offs[e][s] = (l < L && s < n) ? __ldg(chain + (size_t)l * n + s) : -1;
       }
+  }
+  // a warp takes 32 consecutive pixels: one gather + shuffle reduction per pixel, then every
+  // lane decodes and stores the result of "its" pixel (coalesced 8-byte stores)
+  for (long long px0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32; px0 < npx;
+       px0 += (long long)gridDim.x * 8 * 32) {
+   long long mywin = 0;
+   // per-scale offset of the window of pixel px0 + lane, computed by its lane (the divisions
+   // run once per 32 pixels) and broadcast inside the loop
+   int myoff[kRegRatios];
+   {
+     const long long pxl = px0 + lane < npx ? px0 + lane : npx - 1;
+     const int Yl = (int)(pxl / w), Xl = (int)(pxl - (long long)Yl * w);
+#pragma unroll
+     for (int s = 0; s < kRegRatios; ++s) {
+       const int rs = s < n ? R.r[s] : 1;
+       myoff[s] = ((Yl / rs) * (w / rs) + (Xl / rs)) * K;
+     }
+   }
+   for (int j = 0; j < 32 && px0 + j < npx; ++j) {
+    const long long px = px0 + j;
+    const float *base[kMaxRatios];
+    if (in_regs) {
+#pragma unroll
+      for (int s = 0; s < kRegRatios; ++s) base[s] = maps.p[s] + __shfl_sync(0xffffffffu, myoff[s], j);
+    } else {
+      const int Y = (int)(px / w), X = (int)(px % w);
+#pragma unroll
+      for (int s = 0; s < kMaxRatios; ++s)
+        if (s < n) {
+          const int rs = R.r[s];
+          base[s] = maps.p[s] + ((long long)(Y / rs) * (w / rs) + (X / rs)) * K;
+        }
+    }
     float best = -__int_as_float(0x7f800000), vmid = 0.0f;
     int lb = 0x7fffffff;
+    if (in_regs) {
+      const int ne = (L + 31) >> 5;
+#pragma unroll
+      for (int e = 0; e < kLaneEntries; ++e) {
+        const int l = lane + 32 * e;
+        if (e < ne && l < L) {
+          float v = 0.0f;
+          bool first = true;
+#pragma unroll
+          for (int s = kRegRatios - 1; s >= 0; --s)
+            if (s < n && offs[e][s] >= 0) {
+              const float x = __ldg(base[s] + offs[e][s]);
+              v = first ? x : __fadd_rn(x, v);
+              first = false;
+            }
+          if (l + 1 == middle) vmid = v;
+          if (v > best) {
+            best = v;
+            lb = l;
+          }
+        }
+      }
+    } else
     for (int l = lane; l < L; l += 32) {
       const int *off = chain + (size_t)l * n;
       float v = 0.0f;
@@ -285,15 +344,17 @@ ring_argmax_kernel(ScaleMaps maps, const int *chain, int h, int w, int maxh, int
         lb = ol;
       }
     }
-    if (lane == 0) {
-      long long win = lb + 1;
-      if (vmid == best) win = middle;  // opticalflow_model.lua:157-159 with yx2xMulti(0,0)
-      long long oy = 0, ox = 0;
-      decode_spec(R, maxh, maxw, win, &oy, &ox);
-      if (index) index[px] = win;
-      if (flow_y) flow_y[px] = oy;
-      if (flow_x) flow_x[px] = ox;
-    }
+    long long win = lb + 1;
+    if (vmid == best) win = middle;  // opticalflow_model.lua:157-159 with yx2xMulti(0,0)
+    if (lane == j) mywin = win;      // every lane holds the reduced values
+   }
+   if (px0 + lane < npx) {
+     long long oy = 0, ox = 0;
+     decode_spec(R, maxh, maxw, mywin, &oy, &ox);
+     if (index) index[px0 + lane] = mywin;
+     if (flow_y) flow_y[px0 + lane] = oy;
+     if (flow_x) flow_x[px0 + lane] = ox;
+   }
   }
 }
 
@@ -436,6 +497,23 @@ int dm_multiscale_extract(dm_ctx *ctx, const float *const *in1, const float *con
   memset(&maps, 0, sizeof(maps));
   size_t off = 0;
   int rc = DM_OK;
+  // the scales are independent until the ring join: scale 0 stays on the context's stream, the
+  // others alternate over two side streams forked from it (their small grids overlap with the
+  // full-resolution scale instead of queueing behind it)
+  cudaStream_t main_stream = ctx->stream;
+  const bool fork = nratios > 1;
+  if (fork && !ctx->aux[0]) {
+    for (int i = 0; i < 2; ++i) {
+      DM_CUDA(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+      DM_CUDA(cudaEventCreateWithFlags(&ctx->aux_join[i], cudaEventDisableTiming));
+    }
+    DM_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+  }
+  if (fork) {
+    DM_CUDA(cudaEventRecord(ctx->aux_fork, main_stream));
+    for (int i = 0; i < 2; ++i) DM_CUDA(cudaStreamWaitEvent(ctx->aux[i], ctx->aux_fork, 0));
+  }
+  bool used[2] = {false, false};
   for (int i = 0; i < nratios && rc == DM_OK; ++i) {
     dm_pair pr;
     memset(&pr, 0, sizeof(pr));
@@ -448,9 +526,19 @@ int dm_multiscale_extract(dm_ctx *ctx, const float *const *in1, const float *con
     pr.h2 = pr.h1 + maxh - 1;
     pr.w2 = pr.w1 + maxw - 1;
     maps.p[i] = maps_dev + off;
+    if (i > 0) {
+      ctx->stream = ctx->aux[(i - 1) & 1];
+      used[(i - 1) & 1] = true;
+    }
     rc = match_volume_on(call, &pr, maxh, maxw, DM_VOLUME_NEG_SOFTMAX, maps_dev + off);
+    ctx->stream = main_stream;
     off += (size_t)pr.h1 * pr.w1 * K;
   }
+  for (int i = 0; i < 2; ++i)
+    if (used[i]) {
+      cudaEventRecord(ctx->aux_join[i], ctx->aux[i]);
+      cudaStreamWaitEvent(main_stream, ctx->aux_join[i], 0);
+    }
   if (rc == DM_OK) {
     const long long npx = (long long)h * w;
     void *didx = nullptr, *dfy = nullptr, *dfx = nullptr;
@@ -460,7 +548,7 @@ int dm_multiscale_extract(dm_ctx *ctx, const float *const *in1, const float *con
     if (rc == DM_OK) {
       // middle index = yx2xMulti(0, 0): zero flow lives in the scale-1 block
       const int middle = ((maxh + 1) / 2 - 1) * maxw + (maxw + 1) / 2;
-      long long blocks = (npx + 7) / 8;
+      long long blocks = (npx + 255) / 256;  // 8 warps x 32 pixels
       const long long cap = (long long)ctx->num_sms * 16;
       if (blocks > cap) blocks = cap;
       ring_argmax_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(
