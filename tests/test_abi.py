@@ -88,3 +88,36 @@ def test_prepare_input_is_a_view_with_the_reference_offsets(dm):
     a, b = dm.prepareInput(g, f1, f1)
     assert a.shape == (2, 16, 23) and b is f1
     assert np.shares_memory(a, f1) and a[0, 0, 0] == f1[0, 2, 3]  # ceil(5/2)-1, ceil(8/2)-1
+
+
+def _build_c_host(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_abi_host")
+    libdir = os.path.join(ROOT, "depth-estimation_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_host.c"), "-o", exe, "-L", libdir, "-ldepthmatch",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_host_sees_the_error_path(dm, tmp_path):
+    """include/depthmatch.h compiles as pedantic C99, a C program links the library, and without
+    a device dm_create fails with a message instead of falling back or aborting."""
+    import subprocess
+    import torch
+    dm.load()
+    exe = _build_c_host(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present (the gpu variant runs in test_c_host_runs_the_hot_path)")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "no CPU fallback" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_host_runs_the_hot_path(dm, tmp_path):
+    import subprocess
+    dm.load()
+    out = subprocess.run([_build_c_host(tmp_path), "gpu"], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "48 pixels matched" in out.stdout
