@@ -384,6 +384,19 @@ def main():
                                "roofline": {"bound": "hbm", "achieved": va, "peak": hbm_gbs, "unit": "GB/s",
                                             "frac": va / hbm_gbs, "kernel": "match_volume_kernel<10>"}}
 
+    if not args.no_volume:
+        # flow only (index + canvas): no probability is asked for, so the kernel skips the soft-max
+        out_f = {"index": out_d["index"], "flow_full": out_d["flow_full"]}
+        fs = []
+        for _ in range(5):
+            dm.match_extract(in1, f2, MAXH, MAXW, canvas=(H, W), want=("index",), ctx=ctx, out=out_f)
+            fs.append(ctx.last_kernel_ms())
+        torch.cuda.synchronize()
+        fms = float(np.mean(fs[1:]))
+        line["flow_only_mode"] = {"value": B / (fms / 1e3), "unit": "frame-pairs/s (kernels only)", "kernel_ms": fms,
+                                  "outputs": ["index", "flow_full"],
+                                  "alu_frac": ALU_SLOTS * B / (fms / 1e3) / alu_peak}
+
     if not args.no_cpu:
         import oracle_lib as O
         O.build()

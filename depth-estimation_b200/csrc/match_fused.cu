@@ -59,8 +59,17 @@ struct ExtractParams {
 // minimum (and its index), the softmax denominator and -- when SOFT -- the two first
 // moments, all relative to the running minimum (flash-style rescaling when it moves).
 // Shared memory per pixel: the shortlist bitmap [nwords] and the SSD of the zero-flow entry.
-template <bool SOFT, bool DOT>
+enum EpiKind { kEpiScores = 0, kEpiSoft = 1, kEpiWta = 2 };
+
+// EPI: kEpiScores -- argmin + soft-max statistics + thresholded extraction; kEpiSoft -- the same
+// plus the first moments; kEpiWta -- winner-take-all only (index / flow / min_ssd): the arg max
+// of the soft-max is the arg min of the SSD, so when no probability is asked for the
+// exponentials are skipped altogether (the zero-flow tie rule then compares exp(m - v_mid)
+// with 1 instead of the normalised probabilities).
+template <int EPI, bool DOT>
 struct ExtractEpi {
+  static constexpr bool SOFT = EPI == kEpiSoft;
+  static constexpr bool WTA = EPI == kEpiWta;
   static constexpr int kCThreads = ExtractCfg::kCThreads;
   const ExtractParams &P;
   float m[kP], S[kP], sx[kP], sy[kP];
@@ -94,6 +103,11 @@ struct ExtractEpi {
   // a new running minimum v at 1-based index k for pixel p (strict <: the first occurrence
   // wins, like TH max): rescale what was accumulated relative to the old one
   __device__ __forceinline__ void new_min(int p, float v, int k, int bit) {
+    if (WTA) {
+      m[p] = v;
+      idx[p] = k;
+      return;
+    }
     const float sc = ex2_approx((v - m[p]) * kLog2e);  // old m = +inf -> 0
     S[p] *= sc;
     if (SOFT) {
@@ -157,6 +171,7 @@ struct ExtractEpi {
           new_min(p, bm[p], kbase - (p & 1) + rb, bit);
         }
     }
+    if (WTA) return;
     const float rowf = (float)(dy + 1);
     bool cand = false;
     float eb[kP], ebm[kP];
@@ -242,7 +257,7 @@ struct ExtractEpi {
       const int x = x0 + p;
       if (x >= g.W1) continue;
       const size_t o = ((size_t)n * g.H1 + y) * g.W1 + x;
-      const float inv = 1.0f / S[p];
+      const float inv = WTA ? 1.0f : 1.0f / S[p];
       int win = idx[p];
       if ((P.flags & DM_FLAG_TIE_MIDDLE) && win != P.middle) {
         const float emid = expf(m[p] - vmid[p * kCThreads]);
@@ -250,7 +265,7 @@ struct ExtractEpi {
       }
       if (P.index) P.index[o] = win;
       if (P.min_ssd && !DOT) P.min_ssd[o] = m[p];  // kDot: written by tile_rescore
-      if (P.pmax) P.pmax[o] = inv;
+      if (P.pmax && !WTA) P.pmax[o] = inv;
       if (SOFT && P.soft_yx) {
         const size_t plane = (size_t)g.H1 * g.W1;
         const size_t so = (size_t)n * 2 * plane + (size_t)y * g.W1 + x;
@@ -264,7 +279,7 @@ struct ExtractEpi {
         P.flow_full[fo] = (float)(row - P.cy);
         P.flow_full[fo + plane] = (float)(col - P.cx);
       }
-      if (P.todo) {
+      if (P.todo && !WTA) {
         // extractOutput(prob, thr) (extract_output.cpp:63-155).  pmax < thr: nothing qualifies,
         // the pixel stays untouched.  pmax > thr and the runner-up bound e2/S < thr: the list is
         // {pmax}, ret = its position, score = M * pmax (prefix sums of {pmax,0,..}).  Anything within 1e-4 of the threshold, and every pixel that may have
@@ -298,7 +313,7 @@ struct ExtractEpi {
   }
 };
 
-template <int CT, int MODE, bool SOFT>
+template <int CT, int MODE, int EPI>
 __global__ void __launch_bounds__(ExtractCfg::kThreads, 1)
 match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_nb,
                      const ExtractParams P) {
@@ -310,7 +325,7 @@ match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   float *ring = reinterpret_cast<float *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)P.g.nslot * P.g.slab_floats);
   unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
-  ExtractEpi<SOFT, MODE == kDot> epi(P, extra);
+  ExtractEpi<EPI, MODE == kDot> epi(P, extra);
   run_sweep<ExtractCfg, CT, MODE>(&tmap, &tmap_nb, P.g, ring, full, epi);
 }
 
@@ -763,9 +778,11 @@ static int fit_ring(dm_ctx *ctx, SweepGeom *g, int tile_rows, int max_slots, siz
   return DM_OK;
 }
 
-static const void *pick_extract(int CT, int mode, bool soft) {
-#define DM_PICK2(ct, md)                                                   \
-  (soft ? (const void *)match_extract_kernel<ct, md, true> : (const void *)match_extract_kernel<ct, md, false>)
+static const void *pick_extract(int CT, int mode, int epi) {
+#define DM_PICK2(ct, md)                                                                     \
+  (epi == kEpiSoft ? (const void *)match_extract_kernel<ct, md, kEpiSoft>                    \
+                   : (epi == kEpiWta ? (const void *)match_extract_kernel<ct, md, kEpiWta>   \
+                                     : (const void *)match_extract_kernel<ct, md, kEpiScores>))
 #define DM_PICK(ct) (mode == kExact ? DM_PICK2(ct, kExact) : (mode == kDot ? DM_PICK2(ct, kDot) : DM_PICK2(ct, kFma)))
   return CT == 4 ? DM_PICK(4) : (CT == 10 ? DM_PICK(10) : DM_PICK(16));
 #undef DM_PICK
@@ -905,7 +922,8 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
   auto launch = [&](const ExtractParams &Q, const CUtensorMap &nbmap, int mode) -> int {
     const size_t smem = ring_bytes(Q.g, Q.g.nslot) + extra;
-    const void *kfn = pick_extract(pr.CT, mode, Q.soft_yx != nullptr);
+    const bool wta = !Q.pmax && !Q.soft_yx && !Q.todo;  // index / flow / min_ssd only
+    const void *kfn = pick_extract(pr.CT, mode, Q.soft_yx ? kEpiSoft : (wta ? kEpiWta : kEpiScores));
     DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, Q.g.ntiles);
     void *args[] = {(void *)&pr.tmap, (void *)&nbmap, (void *)&Q};
@@ -1057,7 +1075,7 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
   const size_t extra = kBarBytes + (size_t)ExtractCfg::kCThreads * kP * sizeof(unsigned);
   DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
   const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
-  const void *kfn = pick_extract(pr.CT, exact ? kExact : kFma, false);
+  const void *kfn = pick_extract(pr.CT, exact ? kExact : kFma, kEpiScores);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&pr.tmap, (void *)&P};

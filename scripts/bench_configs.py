@@ -77,6 +77,14 @@ def main():
     ms_match = timed(lambda: rm.argmin_flow([f1, f2]))
     res["c4 polar remap 3x360x640 -> 400x416"] = {"ms": ms_remap}
     res["c4 radial match 10x384x400 hWin 15"] = {"ms": ms_match}
+    # north, flow only (winner-take-all epilogue: no soft-max)
+    in2n = torch.randn((16, 10, 360, 640), device="cuda", generator=g)
+    in1n = in2n[:, :, 16:16 + 328, 16:16 + 608] + 0.05 * torch.randn((16, 10, 328, 608), device="cuda", generator=g)
+    outn = {"index": torch.empty((16, 328, 608), dtype=torch.int64, device="cuda"),
+            "flow_full": torch.empty((16, 2, 360, 640), device="cuda")}
+    ms = timed(lambda: dm.match_extract(in1n, in2n, 33, 33, canvas=(360, 640), want=("index",), out=outn))
+    res["north 16 pairs, flow only (index + canvas, no scores)"] = {"ms": ms, "pairs_per_s": 16e3 / ms}
+    del in2n, in1n, outn
     # c5: 1080p, 65x65, one pair and one of 8 row bands
     in2 = torch.randn((10, 1080, 1920), device="cuda", generator=g)
     in1 = in2[:, 32:32 + 1016, 32:32 + 1856] + 0.05 * torch.randn((10, 1016, 1856), device="cuda", generator=g)

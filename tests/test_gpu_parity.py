@@ -916,3 +916,27 @@ def test_multiscale_from_raw_frames(dm, oracle):
     assert ((np.asarray(out["index"]).reshape(-1) != idx) & ~tie).sum() == 0 and tie.mean() < 0.05
     inner = (slice(20, 44), slice(24, 72))
     assert np.median(np.asarray(out["flow_y"])[inner]) == 4 and np.median(np.asarray(out["flow_x"])[inner]) == 4
+
+
+def test_winner_take_all_only_path_equals_the_full_path(dm, oracle, monkeypatch):
+    """When no probability is asked for (index / flow / min_ssd only) the kernel skips the
+    soft-max: same indices, same canvas, same minima as the full epilogue, in every SSD form."""
+    maxh, maxw = 7, 9
+    in1, in2, _ = make_pair(10, 50, 70, maxh, maxw, seed=71, noise=0.4)
+    in1[:, 10:20, 10:30] = 0.25          # a flat patch against a flat patch: ties -> zero flow
+    in2[:, 10:26, 10:38] = 0.25
+    for form in ("diff", "dot"):
+        monkeypatch.setenv("DM_SSD_FORM", form)
+        full = dm.match_extract(in1, in2, maxh, maxw, canvas=(50, 70), want=("index", "min_ssd", "pmax"))
+        wta = dm.match_extract(in1, in2, maxh, maxw, canvas=(50, 70), want=("index", "min_ssd"))
+        np.testing.assert_array_equal(wta["index"], full["index"])
+        np.testing.assert_array_equal(wta["min_ssd"], full["min_ssd"])
+        np.testing.assert_array_equal(wta["flow_full"], full["flow_full"])
+        assert (wta["index"][12:18, 12:28] == dm.getMiddleIndex(dm.Geometry(maxh=maxh, maxw=maxw))).all()
+    monkeypatch.delenv("DM_SSD_FORM")
+    vol = oracle.spatial_matching(in1, in2, maxh, maxw).reshape(-1, maxh * maxw)
+    prob = oracle.neg_softmax(vol)
+    idx, _ = oracle.argmax_tie(prob, maxh * maxw, dm.getMiddleIndex(dm.Geometry(maxh=maxh, maxw=maxw)))
+    gap = oracle.top2_relgap(prob, maxh * maxw)
+    got = dm.match_extract(in1, in2, maxh, maxw, want=("index",), exact=True)["index"].reshape(-1)
+    assert ((got != idx) & (gap >= 1e-5)).sum() == 0
