@@ -529,7 +529,11 @@ class Filter(_Module):
             self._handle_ctx._lib.dm_filter_destroy(self._handle)
         self._handle, self._handle_ctx = None, None
 
-    __del__ = reset_weights
+    def __del__(self):
+        try:  # interpreter shutdown may have torn the library or the context down already
+            self.reset_weights()
+        except Exception:
+            pass
 
     def _layers(self):
         out = []

@@ -940,3 +940,16 @@ def test_winner_take_all_only_path_equals_the_full_path(dm, oracle, monkeypatch)
     gap = oracle.top2_relgap(prob, maxh * maxw)
     got = dm.match_extract(in1, in2, maxh, maxw, want=("index",), exact=True)["index"].reshape(-1)
     assert ((got != idx) & (gap >= 1e-5)).sum() == 0
+
+
+def test_randomised_shapes_forms_and_outputs(dm):
+    """tests/fuzz_parity.py: 30 random (channels, window, frame size, SSD form, noise, flat
+    regions) cases of the fused path -- every output -- against the oracle."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, "fuzz_parity.py"), "5", "30"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "failures: 0" in out.stdout
