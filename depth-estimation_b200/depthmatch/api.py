@@ -512,7 +512,7 @@ class Filter(_Module):
 
     def __init__(self, modules, ctx=None):
         self.modules, self.ctx = list(modules), ctx
-        self._handle, self._handle_ctx = None, None
+        self._handle, self._handle_ctx, self._handle_cin = None, None, None
         self.output = None
 
     def add(self, m):
@@ -546,18 +546,23 @@ class Filter(_Module):
                 out.append([m, 0])
         return out
 
-    def _build(self, c):
-        if self._handle is not None and self._handle_ctx is c:
+    def _build(self, c, cin):
+        if self._handle is not None and self._handle_ctx is c and self._handle_cin == cin:
             return self._handle
         self.reset_weights()
         layers = self._layers()
         arr = (_lib.dm_conv_layer * len(layers))()
         keep = []
+        planes = cin
         for i, (m, tanh) in enumerate(layers):
             w = np.ascontiguousarray(m.weight, np.float32)
             b = np.ascontiguousarray(m.bias, np.float32)
             keep += [w, b]
-            arr[i].n_in, arr[i].n_out, arr[i].kh, arr[i].kw = m.nInputPlane, m.nOutputPlane, m.kH, m.kW
+            # a connection table may leave the last input planes unused (nn.tables.random):
+            # like Torch7, accept an input with more planes than the table mentions
+            n_in = planes if m.connTable is not None and planes >= m.nInputPlane else m.nInputPlane
+            arr[i].n_in, arr[i].n_out, arr[i].kh, arr[i].kw = n_in, m.nOutputPlane, m.kH, m.kW
+            planes = m.nOutputPlane
             arr[i].tanh_after = tanh
             arr[i].weight, arr[i].bias = w.ctypes.data, b.ctypes.data
             if m.connTable is not None:
@@ -570,7 +575,7 @@ class Filter(_Module):
                 raise DepthMatchError(_lib.DM_ERR_INVALID, "SpatialConvolution: weight shape")
         h = C.c_void_p()
         check(c._lib.dm_filter_create(c.handle, arr, len(layers), C.byref(h)))
-        self._handle, self._handle_ctx = h, c
+        self._handle, self._handle_ctx, self._handle_cin = h, c, cin
         return h
 
     def output_size(self, h, w, pads=(0, 0, 0, 0)):
@@ -586,14 +591,14 @@ class Filter(_Module):
         single = len(a.shape) == 3
         shp = (1,) + tuple(a.shape) if single else tuple(a.shape)
         n, cin, h, w = shp
-        fh = self._build(c)
+        convs = [m for m in self.modules if hasattr(m, "weight")]
+        if cin != convs[0].nInputPlane and not (convs[0].connTable is not None and cin > convs[0].nInputPlane):
+            raise DepthMatchError(_lib.DM_ERR_INVALID, "Filter: %d input planes, the first layer takes %d"
+                                  % (cin, convs[0].nInputPlane))
+        fh = self._build(c, cin)
         co, ho, wo = C.c_int(), C.c_int(), C.c_int()
         check(c._lib.dm_filter_output_size(fh, h, w, *[int(v) for v in pads], C.byref(co), C.byref(ho),
                                            C.byref(wo)))
-        convs = [m for m in self.modules if hasattr(m, "weight")]
-        if cin != convs[0].nInputPlane:
-            raise DepthMatchError(_lib.DM_ERR_INVALID, "Filter: %d input planes, the first layer takes %d"
-                                  % (cin, convs[0].nInputPlane))
         optr, out = args.out((n, co.value, ho.value, wo.value), np.float32, like=a)
         check(c._lib.dm_filter_forward(c.handle, fh, iptr, n, h, w, *[int(v) for v in pads], optr))
         self.output = out[0] if single else out

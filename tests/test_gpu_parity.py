@@ -953,3 +953,16 @@ def test_randomised_shapes_forms_and_outputs(dm):
                          text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "failures: 0" in out.stdout
+
+
+def test_randomised_volume_and_filter_cases(dm):
+    """tests/fuzz_volume.py: random shapes of the volume path (SSD and soft-max, exact and FMA)
+    and of single filter layers (full and connection-table, padding, tanh) against the oracle."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, "fuzz_volume.py"), "7", "24"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "failures: 0" in out.stdout
