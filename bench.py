@@ -397,6 +397,34 @@ def main():
                                   "outputs": ["index", "flow_full"],
                                   "alu_frac": ALU_SLOTS * B / (fms / 1e3) / alu_peak}
 
+    if not args.no_volume:
+        # the same path as a frame *stream* (depth_estimation_api.lua keeps the previous frame's
+        # features): every frame crosses PCIe once, pair i = (frame i-1, frame i)
+        # synthetic stream: every frame is a window of one textured canvas moving by a few pixels
+        # per frame (consecutive frames match inside the 33x33 window, like the pairs above)
+        srng = np.random.default_rng(777)
+        canvas_t = srng.standard_normal((C, H + 64, W + 64)).astype(np.float32)
+        offs = np.clip(np.cumsum(srng.integers(-5, 6, (B + 1, 2)), 0), -28, 28) + 32
+        stream_frames = torch.empty((B + 1, C, H, W)).pin_memory()
+        for i, (sy, sx) in enumerate(offs):
+            stream_frames[i] = torch.from_numpy(canvas_t[:, sy:sy + H, sx:sx + W]
+                                                + 0.05 * srng.standard_normal((C, H, W)).astype(np.float32))
+        fs = dm.FeatureStream(MAXH, MAXW, C, H, W, batch=B, want=want, device=torch.cuda.current_device())
+        fs.prime(stream_frames[0])
+        batch_frames = stream_frames[1:]
+        for _ in range(2):
+            h = fs.push(batch_frames)
+        fs.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            h = fs.push(batch_frames)
+        h.wait()
+        fs.synchronize()
+        st = time.perf_counter() - t0
+        line["e2e_stream"] = {"value": B * args.e2e_steps / st, "unit": "frame-pairs/s",
+                              "h2d_bytes_per_step": 4 * B * C * H * W, "d2h_bytes_per_step": int(d2h),
+                              "note": "FeatureStream: frames uploaded once, previous frame resident; rank 0 only"}
+
     if not args.no_cpu:
         import oracle_lib as O
         O.build()

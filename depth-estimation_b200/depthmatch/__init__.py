@@ -22,3 +22,4 @@ from .model_io import (loadCalibration, loadModel, loadTesterNetwork, loadWeight
                        modelDirectory, saveModel, saveNetwork)
 from .depth_estimation_api import DepthEstimationAPI, removeEgoMotion, warpHomography  # noqa: F401
 from .radial_api import RadialTester, polarGeometry  # noqa: F401
+from .stream import FeatureStream  # noqa: F401

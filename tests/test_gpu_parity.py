@@ -966,3 +966,27 @@ def test_randomised_volume_and_filter_cases(dm):
                          text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "failures: 0" in out.stdout
+
+
+def test_feature_stream_equals_independent_pairs(dm):
+    """FeatureStream (every frame uploaded once, the previous one resident) returns, pair by
+    pair, exactly what the independent-pair call returns."""
+    import torch
+    rng = np.random.default_rng(81)
+    C, H, W, mh, mw, B = 4, 40, 56, 5, 7, 3
+    frames = rng.standard_normal((1 + 3 * B, C, H, W)).astype(np.float32)
+    s = dm.FeatureStream(mh, mw, C, H, W, batch=B, want=("index", "pmax", "score_thr"))
+    s.prime(frames[0])
+    pinned = [torch.from_numpy(frames[1 + k * B:1 + (k + 1) * B]).pin_memory() for k in range(3)]
+    handles = [s.push(p) for p in pinned[:2]]
+    got = [{k: v.copy() for k, v in h.wait().items()} for h in handles]     # buffers are reused later
+    got.append({k: v.copy() for k, v in s.push(pinned[2]).wait().items()})
+    s.synchronize()
+    oy, ox = 2, 3
+    for k in range(3):
+        for i in range(B):
+            t = k * B + i                      # pair (frame t, frame t + 1)
+            in1 = np.ascontiguousarray(frames[t][:, oy:oy + H - mh + 1, ox:ox + W - mw + 1])
+            ref = dm.match_extract(in1, frames[t + 1], mh, mw, canvas=(H, W), want=("index", "pmax", "score_thr"))
+            for name in ("index", "pmax", "score_thr", "flow_full"):
+                np.testing.assert_array_equal(got[k][name][i], ref[name], err_msg="%s batch %d pair %d" % (name, k, i))
