@@ -587,8 +587,8 @@ struct VolumeEpi {
           if (f >= base) out[f] = src[(int)((f - base) & 15) * 66 + 2 * it];
         }
         if (last && i < (int)(Gend - E)) {
-          const long long f = E + i;
-          out[f] = src[(int)((f - base) & 15) * 66 + 2 * it];
+          const long long f = E + i;  // a stream shorter than a sector starts after E: mask as above
+          if (f >= base) out[f] = src[(int)((f - base) & 15) * 66 + 2 * it];
         }
       }
     }
