@@ -990,3 +990,16 @@ def test_feature_stream_equals_independent_pairs(dm):
             ref = dm.match_extract(in1, frames[t + 1], mh, mw, canvas=(H, W), want=("index", "pmax", "score_thr"))
             for name in ("index", "pmax", "score_thr", "flow_full"):
                 np.testing.assert_array_equal(got[k][name][i], ref[name], err_msg="%s batch %d pair %d" % (name, k, i))
+
+
+def test_randomised_multiscale_extract_postprocess_and_warps(dm):
+    """tests/fuzz_misc.py: random geometries of the multiscale model, stand-alone extractOutput,
+    postProcessImage / enlargeMask and the LUT / homography warps against the oracle."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, "fuzz_misc.py"), "9", "20"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "failures: 0" in out.stdout
