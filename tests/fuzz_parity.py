@@ -15,7 +15,9 @@ bad_total = 0
 for case in range(n_cases):
     C = int(rng.choice([1, 2, 3, 4, 5, 8, 10, 11, 16, 17, 20]))
     maxh, maxw = int(rng.integers(1, 20)), int(rng.integers(1, 20))
-    H2, W2 = int(rng.integers(maxh + 1, maxh + 40)), int(rng.integers(maxw + 1, maxw + 150))
+    wide = rng.random() < 0.25   # several 128-column tiles and 15-row tile borders
+    H2 = int(rng.integers(maxh + 1, maxh + (70 if wide else 40)))
+    W2 = int(rng.integers(maxw + 1, maxw + (420 if wide else 150)))
     form = rng.choice(["diff", "dot", "exact"])
     noise = float(rng.choice([0.0, 0.05, 0.5]))
     in1, in2, _ = make_pair(C, H2, W2, maxh, maxw, seed=int(rng.integers(1 << 30)), noise=noise)
@@ -29,6 +31,22 @@ for case in range(n_cases):
     want = ("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx")
     got = dm.match_extract(in1, in2, maxh, maxw, want=want, exact=(form == "exact"))
     wta = dm.match_extract(in1, in2, maxh, maxw, want=("index", "min_ssd"), exact=(form == "exact"))
+    if rng.random() < 0.3:
+        # the same pair inside a batch of host buffers (pipelined chunks) and as a strided crop view
+        n = int(rng.integers(2, 7))
+        pos = int(rng.integers(n))
+        b2 = rng.standard_normal((n,) + in2.shape).astype(np.float32)
+        b2[pos] = in2
+        big1 = rng.standard_normal((n, C, in1.shape[1] + 3, in1.shape[2] + 5)).astype(np.float32)
+        big1[pos, :, 1:1 + in1.shape[1], 2:2 + in1.shape[2]] = in1
+        view = big1[:, :, 1:1 + in1.shape[1], 2:2 + in1.shape[2]]
+        batch = dm.match_extract(view, b2, maxh, maxw, want=want, exact=(form == "exact"))
+        for name in want:
+            if not np.array_equal(batch[name][pos], got[name]):
+                print("   batch/view mismatch in", name)
+                got = {k: v[pos] for k, v in batch.items()}
+                got["index"] = got["index"] * 0 - 1
+                break
     vol = O.spatial_matching(in1, in2, maxh, maxw).reshape(-1, K)
     prob = O.neg_softmax(vol)
     middle = (math.ceil(maxh / 2) - 1) * maxw + math.ceil(maxw / 2)
