@@ -121,3 +121,30 @@ def test_c_host_runs_the_hot_path(dm, tmp_path):
     out = subprocess.run([_build_c_host(tmp_path), "gpu"], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "48 pixels matched" in out.stdout
+
+
+def _prototypes(text):
+    """{name: normalised parameter list} of every `dm_*(...)` declaration in a C fragment."""
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(dm_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        out[m.group(1)] = re.sub(r"\s+", " ", m.group(2)).strip()
+    return out
+
+
+def test_lua_ffi_cdef_matches_the_header():
+    """The LuaJIT shim cannot run here; at least its ffi.cdef block must declare the header's
+    functions with the same parameter lists (and nothing the header does not have)."""
+    header = open(os.path.join(ROOT, "include", "depthmatch.h")).read()
+    lua = open(os.path.join(ROOT, "depth-estimation_b200", "lua", "depthmatch_ffi.lua")).read()
+    cdef = lua[lua.index("ffi.cdef[["):lua.index("]]", lua.index("ffi.cdef[["))]
+    h, l = _prototypes(header), _prototypes(cdef)
+    assert set(l) <= set(h), sorted(set(l) - set(h))
+    for name, params in l.items():
+        assert params == h[name], (name, params, h[name])
+    # everything a Lua host needs for the path itself is declared
+    for name in ("dm_create", "dm_destroy", "dm_last_error", "dm_match_volume", "dm_match_extract",
+                 "dm_extract_output", "dm_x2yx_multi", "dm_cascade_add", "dm_multiscale_extract",
+                 "dm_polar_remap", "dm_flow2depth", "dm_filter_create", "dm_filter_forward",
+                 "dm_post_process_image", "dm_enlarge_mask", "dm_warp_homography"):
+        assert name in l, name
