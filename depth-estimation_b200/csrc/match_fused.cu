@@ -66,11 +66,11 @@ enum EpiKind { kEpiScores = 0, kEpiSoft = 1, kEpiWta = 2 };
 // of the soft-max is the arg min of the SSD, so when no probability is asked for the
 // exponentials are skipped altogether (the zero-flow tie rule then compares exp(m - v_mid)
 // with 1 instead of the normalised probabilities).
-template <int EPI, bool DOT>
+template <class Cfg, int EPI, bool DOT>
 struct ExtractEpi {
   static constexpr bool SOFT = EPI == kEpiSoft;
   static constexpr bool WTA = EPI == kEpiWta;
-  static constexpr int kCThreads = ExtractCfg::kCThreads;
+  static constexpr int kCThreads = Cfg::kCThreads;
   const ExtractParams &P;
   float m[kP], S[kP], sx[kP], sy[kP];
   int idx[kP];
@@ -313,8 +313,8 @@ struct ExtractEpi {
   }
 };
 
-template <int CT, int MODE, int EPI>
-__global__ void __launch_bounds__(ExtractCfg::kThreads, 1)
+template <class Cfg, int CT, int MODE, int EPI>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kWarps <= 6 ? 2 : 1)
 match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_nb,
                      const ExtractParams P) {
   if (P.stats) {  // twin launch: the norm bound picks the dot or the difference form
@@ -325,8 +325,8 @@ match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   float *ring = reinterpret_cast<float *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)P.g.nslot * P.g.slab_floats);
   unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
-  ExtractEpi<EPI, MODE == kDot> epi(P, extra);
-  run_sweep<ExtractCfg, CT, MODE>(&tmap, &tmap_nb, P.g, ring, full, epi);
+  ExtractEpi<Cfg, EPI, MODE == kDot> epi(P, extra);
+  run_sweep<Cfg, CT, MODE>(&tmap, &tmap_nb, P.g, ring, full, epi);
 }
 
 // ---------------------------------------------------------------- exact threshold pass
@@ -778,15 +778,18 @@ static int fit_ring(dm_ctx *ctx, SweepGeom *g, int tile_rows, int max_slots, siz
   return DM_OK;
 }
 
-static const void *pick_extract(int CT, int mode, int epi) {
-#define DM_PICK2(ct, md)                                                                     \
-  (epi == kEpiSoft ? (const void *)match_extract_kernel<ct, md, kEpiSoft>                    \
-                   : (epi == kEpiWta ? (const void *)match_extract_kernel<ct, md, kEpiWta>   \
-                                     : (const void *)match_extract_kernel<ct, md, kEpiScores>))
-#define DM_PICK(ct) (mode == kExact ? DM_PICK2(ct, kExact) : (mode == kDot ? DM_PICK2(ct, kDot) : DM_PICK2(ct, kFma)))
+static const void *pick_extract(bool small, int CT, int mode, int epi) {
+#define DM_PICK3(cfg, ct, md)                                                                   \
+  (epi == kEpiSoft ? (const void *)match_extract_kernel<cfg, ct, md, kEpiSoft>                  \
+                   : (epi == kEpiWta ? (const void *)match_extract_kernel<cfg, ct, md, kEpiWta> \
+                                     : (const void *)match_extract_kernel<cfg, ct, md, kEpiScores>))
+#define DM_PICK(ct)                                                                                  \
+  (small ? (mode == kExact ? DM_PICK3(ExtractCfgSmall, ct, kExact) : DM_PICK3(ExtractCfgSmall, ct, kFma)) \
+         : (mode == kExact ? DM_PICK3(ExtractCfg, ct, kExact)                                        \
+                           : (mode == kDot ? DM_PICK3(ExtractCfg, ct, kDot) : DM_PICK3(ExtractCfg, ct, kFma))))
   return CT == 4 ? DM_PICK(4) : (CT == 10 ? DM_PICK(10) : DM_PICK(16));
 #undef DM_PICK
-#undef DM_PICK2
+#undef DM_PICK3
 }
 
 // |x|^2 per pixel over the channels (one FMA chain, k ascending -- the sweep computes |a|^2 the
@@ -844,8 +847,21 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     int rf = call.finish();
     return rc != DM_OK ? rc : rf;
   }
+  // 15-row tiles leave most SMs idle on one small pair: switch to the 5-row configuration
+  const long long big_tiles = (long long)((in->w1 + kTW - 1) / kTW) * ((in->h1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH) *
+                              in->n_pairs;
+  const char *force = getenv("DM_SSD_FORM");  // "diff" / "dot": tuning and tests only
+  // small calls (one 320x180 pair with a 17x17 window) are launch-bound: the norm pre-pass and the
+  // twin launch of the dot form would cost more than it saves
+  const bool big = (double)in->h1 * in->w1 * in->n_pairs * maxh * maxw * in->channels >= 5.0e8 ||
+                   (force && !strcmp(force, "dot"));
+  const bool small = big_tiles < ctx->num_sms && !big && !getenv("DM_NO_SMALL_TILES");
+  const int cfg_th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
+  const int cfg_nslot = small ? ExtractCfgSmall::kNSlot : ExtractCfg::kNSlot;
+  const int cfg_threads = small ? ExtractCfgSmall::kThreads : ExtractCfg::kThreads;
+  const int cfg_cthreads = small ? ExtractCfgSmall::kCThreads : ExtractCfg::kCThreads;
   Prepared pr;
-  DM_CHECK(prepare(call, in, maxh, maxw, ExtractCfg::kTH, &pr));
+  DM_CHECK(prepare(call, in, maxh, maxw, cfg_th, &pr));
   const SweepGeom &g = pr.g;
   const size_t npx = (size_t)g.N * g.H1 * g.W1;
 
@@ -911,7 +927,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     P.vinv = P.vmin + npx;
     DM_CUDA(cudaMemsetAsync(P.ntodo, 0, sizeof(unsigned), ctx->stream));
   }
-  const size_t extra = kBarBytes + (size_t)(P.nwords + 1) * ExtractCfg::kCThreads * kP * sizeof(unsigned);
+  const size_t extra = kBarBytes + (size_t)(P.nwords + 1) * cfg_cthreads * kP * sizeof(unsigned);
   const bool exact = flags & DM_FLAG_EXACT_SSD;
   P.stats = nullptr;
   P.dot_limit = 0.0f;
@@ -919,15 +935,15 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   P.s2n = pr.s2n;
   P.s2c = pr.s2c;
   P.s2y = pr.s2y;
-  DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
+  DM_CHECK(fit_ring(ctx, &P.g, cfg_th, cfg_nslot, extra));
   auto launch = [&](const ExtractParams &Q, const CUtensorMap &nbmap, int mode) -> int {
     const size_t smem = ring_bytes(Q.g, Q.g.nslot) + extra;
     const bool wta = !Q.pmax && !Q.soft_yx && !Q.todo;  // index / flow / min_ssd only
-    const void *kfn = pick_extract(pr.CT, mode, Q.soft_yx ? kEpiSoft : (wta ? kEpiWta : kEpiScores));
+    const void *kfn = pick_extract(small, pr.CT, mode, Q.soft_yx ? kEpiSoft : (wta ? kEpiWta : kEpiScores));
     DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, Q.g.ntiles);
+    const int grid = grid_for(ctx, kfn, cfg_threads, smem, Q.g.ntiles);
     void *args[] = {(void *)&pr.tmap, (void *)&nbmap, (void *)&Q};
-    DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(ExtractCfg::kThreads), args, smem, ctx->stream));
+    DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(cfg_threads), args, smem, ctx->stream));
     count_launch(ctx);
     return DM_OK;
   };
@@ -935,18 +951,14 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   // is a few ulp of |a|^2 + |b|^2.  It is used when the largest norms keep that error under
   // ~1e-5 (the parity bar on the soft-max scores): a pre-pass writes |b|^2 per frame-2 pixel and
   // the maxima, then both kernels are launched and the device-side bound lets one of them run.
-  const char *force = getenv("DM_SSD_FORM");  // "diff" / "dot": tuning and tests only
-  // small calls (one 320x180 pair with a 17x17 window) are launch-bound: the pre-pass and the
-  // twin launch would cost more than the dot form saves
-  const bool big = (double)npx * maxh * maxw * pr.Cin >= 5.0e8 || (force && !strcmp(force, "dot"));
-  const bool allow_dot = big && !exact && !(flags & DM_FLAG_DIFF_SSD) && !(force && !strcmp(force, "diff"));
+  const bool allow_dot = big && !small && !exact && !(flags & DM_FLAG_DIFF_SSD) && !(force && !strcmp(force, "diff"));
   bool twin = false;
   ExtractParams Pd = P;
   CUtensorMap nbmap;
   if (allow_dot) {
     Pd.g.nb_off = (Pd.g.C * Pd.g.WB + 31) & ~31;
     Pd.g.slab_floats = Pd.g.nb_off + ((Pd.g.WB + 31) & ~31);
-    twin = fit_ring(ctx, &Pd.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra) == DM_OK;
+    twin = fit_ring(ctx, &Pd.g, cfg_th, cfg_nslot, extra) == DM_OK;
   }
   if (twin) {
     const long long w2p = (g.W2 + 3) & ~3LL;
@@ -1075,7 +1087,7 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
   const size_t extra = kBarBytes + (size_t)ExtractCfg::kCThreads * kP * sizeof(unsigned);
   DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
   const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
-  const void *kfn = pick_extract(pr.CT, exact ? kExact : kFma, kEpiScores);
+  const void *kfn = pick_extract(false, pr.CT, exact ? kExact : kFma, kEpiScores);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&pr.tmap, (void *)&P};

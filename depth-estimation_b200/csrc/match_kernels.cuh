@@ -39,6 +39,9 @@ struct SweepCfg {
   static constexpr int kNSlot = NW + PF;
 };
 using ExtractCfg = SweepCfg<15, 8>;  // fused extraction: registers allow 16 warps of 128
+// the same kernel for calls too small to fill the machine with 15-row tiles (one robot-size
+// frame pair): 5-row tiles, 6 warps, two or three CTAs per SM
+using ExtractCfgSmall = SweepCfg<5, 8>;
 using VolumeCfg = SweepCfg<12, 4>;   // volume output: leaves shared memory for the store staging
 
 // Block schedule for a window width.  Displacements are swept in "skewed" blocks: in block

@@ -26,6 +26,9 @@ for case in range(n_cases):
         in2[:, : in2.shape[1] // 2] = 0.5
     K = maxh * maxw
     os.environ.pop("DM_SSD_FORM", None)
+    os.environ.pop("DM_NO_SMALL_TILES", None)
+    if rng.random() < 0.5:   # small inputs take 5-row tiles by default: keep the 15-row kernels covered
+        os.environ["DM_NO_SMALL_TILES"] = "1"
     if form in ("diff", "dot"):
         os.environ["DM_SSD_FORM"] = form
     want = ("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx")
@@ -70,8 +73,17 @@ for case in range(n_cases):
     h1, w1 = in1.shape[1:]
     ret, sc, _ = O.extract_output(prob.reshape(h1, w1, K), 0.11, np.zeros((h1, w1), np.int64), np.zeros((h1, w1), np.float32))
     near = (np.abs(prob - 0.11) < 2e-4).any(-1).reshape(h1, w1)
-    if ((got["index_thr"] != ret) & ~near).any() or not np.allclose(got["score_thr"][~near], sc[~near], rtol=1e-4, atol=1e-6):
+    tie2 = tie.reshape(h1, w1)   # the two largest probabilities within 1e-5: either may lead the list
+    if ((got["index_thr"] != ret) & ~near & ~tie2).any() or \
+            not np.allclose(got["score_thr"][~near], sc[~near], rtol=1e-4, atol=1e-6):
         errs.append("thr")
+        if len(sys.argv) > 3:   # verbose: where and what
+            badpx = np.argwhere((((got["index_thr"] != ret) & ~tie2) | ~np.isclose(got["score_thr"], sc, rtol=1e-4, atol=1e-6)) & ~near)
+            print("   small tiles off:", os.environ.get("DM_NO_SMALL_TILES"), "bad pixels", badpx[:6].tolist())
+            for (yy, xx) in badpx[:3]:
+                pr = prob.reshape(h1, w1, K)[yy, xx]
+                print("   px", yy, xx, "got", got["index_thr"][yy, xx], got["score_thr"][yy, xx], "want", ret[yy, xx], sc[yy, xx],
+                      "probs>0.1:", [(int(k) + 1, float(pr[k])) for k in np.nonzero(pr > 0.1)[0]])
     status = "ok" if not errs else "FAIL " + ",".join(errs)
     bad_total += bool(errs)
     print("case %2d C=%2d win=%2dx%2d in2=%3dx%3d form=%-5s noise=%.2f ties=%d: %s"
