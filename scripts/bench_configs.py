@@ -38,6 +38,13 @@ def main():
     res["c1 raw frames 3x180x320: filter + 17x17 match (1 pair)"] = {"ms": ms, "pairs_per_s": 1e3 / ms}
     ms = timed(lambda: flt.forward(fr))
     res["c1 filter alone (both frames)"] = {"ms": ms}
+    # the robot-host function (depth_estimation_api.lua:nextFrameDepth) on device-resident 320x180 frames
+    geoA = dm.Geometry(layers=[[3, 5, 5, 8], [4, 16, 16, 10]], maxh=17, maxw=17, hImg=180, wImg=320)
+    apiA = dm.DepthEstimationAPI(geoA, dm.getFilter(geoA, np.random.default_rng(2)),
+                                 K=np.array([[293.8, 0, 310.4], [0, 300.6, 251.6], [0, 0, 1.0]]), first_frame=fr[0])
+    Rm = np.eye(3)
+    ms = timed(lambda: apiA.nextFrameDepth(fr[1], R=Rm, nFound=100, nInliers=90))
+    res["nextFrameDepth 3x180x320 (warp, filter, match volume, mean extraction, masks)"] = {"ms": ms, "frames_per_s": 1e3 / ms}
     # c2: 64 pairs of 320x180, 33x33
     in2 = torch.randn((64, 10, 180, 320), device="cuda", generator=g)
     in1 = in2[:, :, 16:16 + 148, 16:16 + 288] + 0.05 * torch.randn((64, 10, 148, 288), device="cuda", generator=g)
