@@ -1003,3 +1003,31 @@ def test_randomised_multiscale_extract_postprocess_and_warps(dm):
                          text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "failures: 0" in out.stdout
+
+
+def test_device_calls_are_stream_ordered_and_graph_capturable(dm):
+    """A call on device buffers does no host synchronisation, allocation or pageable copy once
+    the arena is warm: it can be captured in a CUDA graph and replayed with the same result."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(1)
+    in2 = torch.randn((2, 10, 60, 140), device="cuda", generator=g)
+    in1 = (in2[:, :, 4:4 + 52, 4:4 + 132] + 0.05 * torch.randn((2, 10, 52, 132), device="cuda", generator=g)).contiguous()
+    ctx = dm.Context(0)
+    want = ("index", "pmax", "score_thr")
+    out = {"index": torch.empty((2, 52, 132), dtype=torch.int64, device="cuda"),
+           "pmax": torch.empty((2, 52, 132), device="cuda"), "score_thr": torch.empty((2, 52, 132), device="cuda")}
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            dm.match_extract(in1, in2, 9, 9, want=want, ctx=ctx, out=out)
+    s.synchronize()
+    ref = {k: v.clone() for k, v in out.items()}
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        dm.match_extract(in1, in2, 9, 9, want=want, ctx=ctx, out=out)
+    for v in out.values():
+        v.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for k in out:
+        assert torch.equal(out[k], ref[k]), k
