@@ -11,9 +11,13 @@
 //   y,x   = sum_k p_k*row_k, sum_k p_k*col_k            OutputExtractor.lua:21-35
 //   flow  = (row,col) - ceil(max/2), pasted in a canvas processOutput        (:201-252)
 //
-// Numerics: SSD in fp32, channel-ascending, FMA-contracted unless DM_FLAG_EXACT_SSD;
-// the softmax runs online (flash-style running minimum) with ex2.approx, so
-// probabilities agree with the two-pass CPU path to ~1e-6 relative, not bit-wise.
+// Numerics: SSD in fp32, channel-ascending.  Three forms (SsdMode, match_kernels.cuh): the
+// difference form with FMA contraction, the same with separately rounded multiply and add
+// (DM_FLAG_EXACT_SSD, bit-exact with the CPU path), and for large calls |a|^2+|b|^2-2a.b behind a
+// device-side bound on the norms (half the FP32 work, absolute error a few ulp of the norms).
+// The softmax runs online (flash-style running minimum) with ex2.approx, so probabilities agree
+// with the two-pass CPU path to ~1e-6 relative, not bit-wise.  When no probability is asked for
+// (index / flow / min_ssd only) the exponentials are skipped altogether (kEpiWta).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>

@@ -1,8 +1,9 @@
 // match_kernels.cuh -- the tiled SSD sweep shared by the fused extract kernel and
 // the volume kernel.
 //
-// Work decomposition (one CTA = 15 consumer warps (+1 TMA producer warp) = a tile of TH=15 output rows x TW=128
-// output columns of one frame pair):
+// Work decomposition (one CTA = NW consumer warps + 1 TMA producer warp = a tile of TH = NW output
+// rows x TW = 128 output columns of one frame pair; NW = 15 or 5 for the fused kernel, 12 for the
+// volume kernel, see SweepCfg):
 //   * warp w owns output row y0+w; lane l owns P=4 consecutive pixels x0+4l..x0+4l+3
 //     whose C feature values (frame 1) stay in registers for the whole sweep;
 //   * the sweep runs dy = 0..maxh-1.  At step dy warp w needs frame-2 row
@@ -10,11 +11,11 @@
 //     [C][WB] floats.  Slabs stream through a ring of NSLOT shared-memory slots
 //     filled by TMA (cp.async.bulk.tensor 4-D box {WB,1,C,1}, zero fill outside
 //     the frame) and signalled through one mbarrier per slot, so a CTA holds
-//     only TH+4 rows of the halo at any time, whatever the window height;
-//   * inside a step the dx range is cut in blocks of R=8 (the last one masked when
-//     the width is not a multiple of 8; a width of 8n+1 ends with one single
-//     column instead): a thread turns P+R-1 = 11 floats of the slab (3 LDS.128)
-//     into P*R = 32 SSD partial sums per channel -- 64 FSUB+FFMA per 3 loads.
+//     only NSLOT rows of the halo at any time, whatever the window height;
+//   * inside a step the dx range is cut in skewed blocks of R=8 (BlockSchedule: the last one
+//     masked, or 2 wide when at most two columns are left): a thread turns 12 floats of the
+//     slab (3 LDS.128) into P*R = 32 SSD partial sums per channel with packed fp32 -- 16 FADD2 +
+//     16 FFMA2, or 16 FFMA2 alone in the dot form.
 // The per-block epilogue is supplied by the caller (extract or volume).
 #pragma once
 
