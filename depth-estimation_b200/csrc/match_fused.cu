@@ -44,6 +44,8 @@ struct ExtractParams {
   long long *index_thr;
   float *score_thr, *soft_yx;
   unsigned long long *n_untouched;
+  float *conf_marginal;  // kEpiSoft: 1 where max_dy sum_dx p(dy,dx) > prob_threshold
+  float p_thr;           // prob_threshold as float
   // thresholded extraction (extractOutput on the probabilities), see ExtractEpi::tile_end
   int nwords;           // 32-bit words of the per-pixel (dy, dx-block) shortlist bitmap
   int gb;               // consecutive blocks that share one shortlist bit (1 unless the window is huge)
@@ -77,6 +79,8 @@ struct ExtractEpi {
   static constexpr int kCThreads = Cfg::kCThreads;
   const ExtractParams &P;
   float m[kP], S[kP], sx[kP], sy[kP];
+  float rowsum[SOFT ? kP : 1], rowmax[SOFT ? kP : 1];  // kEpiSoft: marginal over dx of the current
+                                                        // window row, and the largest one so far
   int idx[kP];
   // thresholded extraction: e2[p] = upper bound of the second largest exp(m - v) seen so far
   // (relative to the running minimum, rescaled with it); vfrom[p] = first shortlist bit still
@@ -96,6 +100,7 @@ struct ExtractEpi {
     for (int p = 0; p < kP; ++p) {
       m[p] = __int_as_float(0x7f800000);
       S[p] = sx[p] = sy[p] = 0.0f;
+      if (SOFT) rowsum[p] = rowmax[p] = 0.0f;
       idx[p] = 1;
       e2[p] = 0.0f;
       vfrom[p] = 0;
@@ -117,6 +122,8 @@ struct ExtractEpi {
     if (SOFT) {
       sx[p] *= sc;
       sy[p] *= sc;
+      rowsum[p] *= sc;
+      rowmax[p] *= sc;
     }
     e2[p] = fmaxf(e2[p], 1.0f) * sc;  // the old minimum (e = 1) becomes a runner-up
     // old minimum (and everything before it) below the threshold for good: earlier bits are dead
@@ -203,6 +210,11 @@ struct ExtractEpi {
         if (SOFT) {
           sx[p] += fmaf(eb[p], (float)(dx0 - (p & 1)), ex);  // column = dx + 1
           sy[p] = fmaf(eb[p], rowf, sy[p]);
+          rowsum[p] += eb[p];
+          if (blk == P.g.bs.per_row() - 1) {  // the window row is complete (warp-uniform)
+            rowmax[p] = fmaxf(rowmax[p], rowsum[p]);
+            rowsum[p] = 0.0f;
+          }
         }
         // thresholded extraction: p_k(final) <= e_k / S(now), so an entry of this block can
         // end above the threshold only if the block's largest e exceeds thr * S
@@ -270,6 +282,7 @@ struct ExtractEpi {
       if (P.index) P.index[o] = win;
       if (P.min_ssd && !DOT) P.min_ssd[o] = m[p];  // kDot: written by tile_rescore
       if (P.pmax && !WTA) P.pmax[o] = inv;
+      if (SOFT && P.conf_marginal) P.conf_marginal[o] = rowmax[p] * inv > P.p_thr ? 1.0f : 0.0f;
       if (SOFT && P.soft_yx) {
         const size_t plane = (size_t)g.H1 * g.W1;
         const size_t so = (size_t)n * 2 * plane + (size_t)y * g.W1 + x;
@@ -847,6 +860,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
                w_img, in->h1, in->w1);
   Call call(ctx, defer);
   if (in->channels > kMaxC) {
+    DM_REQUIRE(!out->conf_marginal, "dm_match_extract: conf_marginal is not available beyond %d channels", kMaxC);
     int rc = generic_match_extract(call, in, maxh, maxw, flags, prob_threshold, h_img, w_img, out);
     int rf = call.finish();
     return rc != DM_OK ? rc : rf;
@@ -901,7 +915,11 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   DM_OUT(index_thr, long long, npx * 8)
   DM_OUT(score_thr, float, npx * 4)
   DM_OUT(soft_yx, float, npx * 2 * 4)
+  DM_OUT(conf_marginal, float, npx * 4)
 #undef DM_OUT
+  P.p_thr = (float)prob_threshold;
+  DM_REQUIRE(!P.conf_marginal || P.soft_yx, "dm_match_extract: conf_marginal belongs to the 'mean' extraction: "
+                                           "ask for soft_yx too");
   P.n_untouched = nullptr;
   if (out->n_untouched) {
     DM_CHECK(call.out(out->n_untouched, (size_t)g.N * 8, &p));
@@ -1059,6 +1077,7 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
     if (so.index_thr) so.index_thr += n0 * npx1;
     if (so.score_thr) so.score_thr += n0 * npx1;
     if (so.soft_yx) so.soft_yx += n0 * 2 * npx1;
+    if (so.conf_marginal) so.conf_marginal += n0 * npx1;
     if (so.n_untouched) so.n_untouched += n0;
     rc = match_extract_impl(ctx->pipe[c & 1], &sub, maxh, maxw, flags, prob_threshold, h_img, w_img, &so,
                             true);

@@ -33,7 +33,7 @@ class dm_pair(C.Structure):
 class dm_extract_out(C.Structure):
     _fields_ = [("index", C.c_void_p), ("min_ssd", C.c_void_p), ("pmax", C.c_void_p),
                 ("flow_full", C.c_void_p), ("index_thr", C.c_void_p), ("score_thr", C.c_void_p),
-                ("soft_yx", C.c_void_p), ("n_untouched", C.c_void_p)]
+                ("soft_yx", C.c_void_p), ("n_untouched", C.c_void_p), ("conf_marginal", C.c_void_p)]
 
 
 class dm_conv_layer(C.Structure):

@@ -217,7 +217,7 @@ def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_thres
     shapes = {"index": ((N, H1, W1), np.int64), "min_ssd": ((N, H1, W1), np.float32),
               "pmax": ((N, H1, W1), np.float32), "index_thr": ((N, H1, W1), np.int64),
               "score_thr": ((N, H1, W1), np.float32), "soft_yx": ((N, 2, H1, W1), np.float32),
-              "n_untouched": ((N,), np.int64)}
+              "n_untouched": ((N,), np.int64), "conf_marginal": ((N, H1, W1), np.float32)}
     want = list(want)
     if canvas is not None and "flow_full" not in want:
         want.append("flow_full")
@@ -792,7 +792,7 @@ class DenseMatch(_Module):
         self.output = FusedOutput(match_extract(inp[0], inp[1], g.maxh, g.maxw, tie_middle=True,
                                                 exact=self.exact, canvas=canvas, ctx=self.ctx,
                                                 want=("index", "pmax", "index_thr", "score_thr",
-                                                      "soft_yx")))
+                                                      "soft_yx", "conf_marginal")))
         return self.output
 
 
@@ -878,7 +878,10 @@ def processOutput(geometry, output, process_full=None, threshold=None, ctx=None)
             fy = _floor(output["soft_yx"][..., 0, :, :] + 0.5)
             fx = _floor(output["soft_yx"][..., 1, :, :] + 0.5)
             ret["index"] = _to_long(yx2x(geometry, fy, fx))
-            ret["confidences"] = _ones_like(ret["index"])
+            if "conf_marginal" in output:     # getOutputConfidences2's marginal test, fused
+                ret["confidences"] = output["conf_marginal"] > 0
+            else:
+                ret["confidences"] = _ones_like(ret["index"])
         else:
             if threshold is None:
                 ret["index"] = output["index"]

@@ -57,12 +57,15 @@ class DepthEstimationAPI:
 
     bad_image_threshold = 0.2  # nInliers / nFound (:158)
 
-    def __init__(self, geometry, filter, K=None, first_frame=None, ctx=None):
+    def __init__(self, geometry, filter, K=None, first_frame=None, fused=True, ctx=None):
         self.geometry = api.Geometry(geometry)
         self.geometry.prefilter = True
         self.geometry.output_extraction_method = "mean"       # :31
         self.filter, self.ctx = filter, ctx
-        self.model = api._MatchModel(api.Geometry(self.geometry, output_extraction_method="max"), ctx=ctx)
+        # fused: one kernel gives the soft mean and the marginal confidence (no volume in HBM);
+        # fused=False walks the reference's graph: probability volume, then processOutput on it
+        self.model = api.DenseMatch(self.geometry, ctx=ctx) if fused else \
+            api._MatchModel(api.Geometry(self.geometry, output_extraction_method="max"), ctx=ctx)
         self.Khalf = None
         if K is not None:
             self.Khalf = np.asarray(K, np.float64).reshape(3, 3) * 0.5

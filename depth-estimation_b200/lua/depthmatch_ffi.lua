@@ -17,6 +17,7 @@ typedef struct dm_pair {
 typedef struct dm_extract_out {
   int64_t *index; float *min_ssd; float *pmax; float *flow_full;
   int64_t *index_thr; float *score_thr; float *soft_yx; int64_t *n_untouched;
+  float *conf_marginal;
 } dm_extract_out;
 int dm_version(void);
 const char *dm_last_error(void);

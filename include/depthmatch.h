@@ -117,6 +117,9 @@ typedef struct dm_extract_out {
   float *score_thr;    /* extractOutput scores; 0 where untouched */
   float *soft_yx;      /* [n][2][h1][w1]: OutputExtractor y, x (1-based, sub-pixel) (OutputExtractor.lua:21-35) */
   int64_t *n_untouched; /* [n_pairs] pixels extractOutput would have left untouched */
+  float *conf_marginal; /* getOutputConfidences2's confidence (opticalflow_model.lua:186-195): 1 where
+                           some row marginal sum_dx p(dy, dx) exceeds prob_threshold, else 0.
+                           Needs soft_yx (the 'mean' extraction it belongs to) */
 } dm_extract_out;
 
 /* Replaces prepareInput + model:forward + processOutput

@@ -44,7 +44,7 @@ def main():
                                  K=np.array([[293.8, 0, 310.4], [0, 300.6, 251.6], [0, 0, 1.0]]), first_frame=fr[0])
     Rm = np.eye(3)
     ms = timed(lambda: apiA.nextFrameDepth(fr[1], R=Rm, nFound=100, nInliers=90))
-    res["nextFrameDepth 3x180x320 (warp, filter, match volume, mean extraction, masks)"] = {"ms": ms, "frames_per_s": 1e3 / ms}
+    res["nextFrameDepth 3x180x320 (warp, filter, fused match + mean extraction, masks)"] = {"ms": ms, "frames_per_s": 1e3 / ms}
     # c2: 64 pairs of 320x180, 33x33
     in2 = torch.randn((64, 10, 180, 320), device="cuda", generator=g)
     in1 = in2[:, :, 16:16 + 148, 16:16 + 288] + 0.05 * torch.randn((64, 10, 148, 288), device="cuda", generator=g)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(dm):
 def test_struct_layout_matches_header(dm):
     from depthmatch import _lib
     assert C.sizeof(_lib.dm_pair) == 2 * 8 + 6 * 4 + 6 * 8
-    assert C.sizeof(_lib.dm_extract_out) == 8 * 8
+    assert C.sizeof(_lib.dm_extract_out) == 9 * 8
 
 
 def test_version_and_error_string(dm):

@@ -1031,3 +1031,31 @@ def test_device_calls_are_stream_ordered_and_graph_capturable(dm):
     torch.cuda.synchronize()
     for k in out:
         assert torch.equal(out[k], ref[k]), k
+
+
+def test_fused_mean_extraction_with_marginal_confidence(dm, oracle):
+    """'mean' extraction (OutputExtractor + getOutputConfidences2's marginal-over-x threshold test,
+    opticalflow_model.lua:171-199) out of the fused kernel, against the oracle on the volume."""
+    maxh, maxw = 15, 5
+    in1, in2, _ = make_pair(10, 56, 150, maxh, maxw, seed=91, noise=0.3)
+    # left half: low-contrast features -> flat soft-max, every row marginal ~1/15 < 0.11
+    in1[:, :, :70] *= 0.05
+    in2[:, :, :72] *= 0.05
+    got = dm.match_extract(in1, in2, maxh, maxw, want=("soft_yx", "conf_marginal", "pmax"))
+    prob = oracle.neg_softmax(oracle.spatial_matching(in1, in2, maxh, maxw))
+    h1, w1 = in1.shape[1:]
+    ym, xm = oracle.soft_mean(prob, maxh, maxw)
+    np.testing.assert_allclose(got["soft_yx"][0].reshape(-1), ym, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(got["soft_yx"][1].reshape(-1), xm, rtol=1e-4, atol=1e-4)
+    pm = oracle.marginal_x(prob, maxh, maxw).reshape(h1, w1, maxh)
+    _, sc, _ = oracle.extract_output(pm, 0.11, np.zeros((h1, w1), np.int64), np.zeros((h1, w1), np.float32))
+    near = np.abs(pm.max(-1) - 0.11) < 1e-4
+    want = (sc > 0).astype(np.float32)
+    assert 0.02 < want.mean() < 0.98           # both classes are exercised
+    np.testing.assert_array_equal(got["conf_marginal"][~near], want[~near])
+    with pytest.raises(dm.DepthMatchError):
+        dm.match_extract(in1, in2, maxh, maxw, want=("index", "conf_marginal"))
+    # the processOutput mirror picks it up for output_extraction_method = 'mean'
+    g = dm.Geometry(maxh=maxh, maxw=maxw, hImg=56, wImg=150, output_extraction_method="mean")
+    po = dm.processOutput(g, dm.getModel(g, True, True, fused=True).forward([in1, in2]), True, None)
+    np.testing.assert_array_equal(np.asarray(po["confidences"])[~near], want[~near] > 0)
