@@ -39,6 +39,7 @@ K = MAXH * MAXW
 BYTES_FUSED = 4 * C * (H1 * W1 + H * W) + 12 * H1 * W1
 BYTES_VOLUME = BYTES_FUSED + 4 * H1 * W1 * K
 ALU_SLOTS = 2 * C * K * H1 * W1
+NCU_DRAM_BYTES_PER_PAIR = (75.497216e6 + 3.643392e6) / 4   # profiles/r01_ncu_fused_kernel.md, dot-form kernel
 METRIC = "frame-pairs/sec @640x360, 33x33 window"
 WORKLOAD = "north: 640x360 feature maps, C=10, 33x33 window, fused match+extract"
 
@@ -350,7 +351,11 @@ def main():
                    "outputs": list(want) + ["flow_full"],
                    "l2": "inputs per step (%.0f MB) larger than the 126 MB L2" % (B * 2 * C * H * W * 4 / 1e6)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": achieved / hbm_gbs, "traffic": None, "peak_source": which,
+                     "frac": achieved / hbm_gbs,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the round's
+                     # `ncu --set full` capture (4 pairs per launch: 75.5 MB + 3.6 MB), per pair x B
+                     "traffic": NCU_DRAM_BYTES_PER_PAIR * B, "traffic_unit": "bytes per launch",
+                     "algorithmic_bytes": BYTES_FUSED * B, "peak_source": which,
                      "kernel": "match_extract_kernel<10>", "kernel_ms": k_ms,
                      "note": "fused mode never writes the volume: compulsory traffic is tiny and the "
                              "binding roof is the FP32 pipe, see alu"},
