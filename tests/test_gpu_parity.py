@@ -1059,3 +1059,52 @@ def test_fused_mean_extraction_with_marginal_confidence(dm, oracle):
     g = dm.Geometry(maxh=maxh, maxw=maxw, hImg=56, wImg=150, output_extraction_method="mean")
     po = dm.processOutput(g, dm.getModel(g, True, True, fused=True).forward([in1, in2]), True, None)
     np.testing.assert_array_equal(np.asarray(po["confidences"])[~near], want[~near] > 0)
+
+
+def test_no_writes_outside_the_output_buffers(dm):
+    """Guard bands: every output of the fused call and the volume are carved out of sentinel-filled
+    device buffers; after the calls the bands are intact (compute-sanitizer is not available on
+    this pool, so out-of-bounds stores are looked for this way), for ragged shapes and both tile
+    configurations."""
+    import ctypes as C
+    import torch
+    from depthmatch import _lib
+    rng = np.random.default_rng(101)
+    G = 4096   # guard band, elements
+    for (n, c, h2, w2, mh, mw) in [(1, 10, 23, 141, 5, 9), (3, 4, 40, 67, 7, 1), (2, 16, 19, 300, 3, 17),
+                                   (1, 3, 9, 5, 2, 1), (5, 10, 52, 135, 9, 9)]:
+        h1, w1 = h2 - mh + 1, w2 - mw + 1
+        in2 = torch.from_numpy(rng.standard_normal((n, c, h2, w2)).astype(np.float32)).cuda()
+        in1 = torch.from_numpy(rng.standard_normal((n, c, h1, w1)).astype(np.float32)).cuda()
+        shapes = {"index": ((n, h1, w1), torch.int64), "min_ssd": ((n, h1, w1), torch.float32),
+                  "pmax": ((n, h1, w1), torch.float32), "index_thr": ((n, h1, w1), torch.int64),
+                  "score_thr": ((n, h1, w1), torch.float32), "soft_yx": ((n, 2, h1, w1), torch.float32),
+                  "conf_marginal": ((n, h1, w1), torch.float32), "flow_full": ((n, 2, h2, w2), torch.float32)}
+        bufs, out = {}, {}
+        for k, (shp, dt) in shapes.items():
+            numel = int(np.prod(shp))
+            sentinel = -12345 if dt == torch.int64 else -12345.5
+            b = torch.full((numel + 2 * G,), sentinel, dtype=dt, device="cuda")
+            bufs[k] = (b, sentinel, numel)
+            out[k] = b[G:G + numel].view(shp)
+        dm.match_extract(in1, in2, mh, mw, canvas=(h2, w2), out=out,
+                         want=("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx", "conf_marginal"))
+        torch.cuda.synchronize()
+        for k, (b, sentinel, numel) in bufs.items():
+            assert bool((b[:G] == sentinel).all()) and bool((b[G + numel:] == sentinel).all()), (k, n, c, h2, w2, mh, mw)
+            assert not bool((out[k] == sentinel).any()), k
+        # the volume, through the C ABI with a raw pointer into a guarded buffer
+        K = mh * mw
+        numel = n * h1 * w1 * K
+        vb = torch.full((numel + 2 * G,), -12345.5, device="cuda")
+        ctx = dm.default_context()
+        p = _lib.dm_pair()
+        p.in1, p.in2 = in1.data_ptr(), in2.data_ptr()
+        p.n_pairs, p.channels, p.h1, p.w1, p.h2, p.w2 = n, c, h1, w1, h2, w2
+        for mode in (0, 1):
+            vb.fill_(-12345.5)
+            ctx.use_stream(torch.cuda.current_stream().cuda_stream)
+            dm.api.check(ctx._lib.dm_match_volume(ctx.handle, C.byref(p), mh, mw, mode, C.c_void_p(vb.data_ptr() + 4 * G)))
+            torch.cuda.synchronize()
+            assert bool((vb[:G] == -12345.5).all()) and bool((vb[G + numel:] == -12345.5).all()), ("volume", mode, n, c, h2, w2)
+            assert not bool((vb[G:G + numel] == -12345.5).any())
