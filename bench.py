@@ -324,6 +324,9 @@ def main():
         c.synchronize()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the host-buffer path returned what the device-buffer path computed (outside the timed region)
+    for o in outs:
+        assert np.array_equal(o["index"], out["index"].cpu().numpy()), "e2e result differs from the device path"
     te = torch.tensor([e2e_s], device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
