@@ -72,8 +72,50 @@ def calibration_vectors():
     np.savez_compressed(os.path.join(HERE, "ref_calibration.npz"), **out)
 
 
+def c1_cars_vectors():
+    """oracle_c1_cars.npz: BASELINE config 1 -- the reference's own test pair celiu/car1.jpg,
+    car2.jpg (640x480), scaled to 320x180 like opticalflow.lua:139-140, through the default
+    two-layer filter {3,5,5,8} tanh {4,16,16,10} with seeded random-init weights and a 17x17
+    window.  Frames are stored as uint8 RGB at 320x180; features, volume statistics and indices
+    come from the oracle (Torch7 is not available to run the reference itself)."""
+    import cv2
+    rng = np.random.default_rng(1)
+    frames = []
+    for name in ("car1.jpg", "car2.jpg"):
+        bgr = cv2.imread(os.path.join("/root/reference/celiu", name), cv2.IMREAD_COLOR)
+        assert bgr is not None and bgr.shape == (480, 640, 3), name
+        small = cv2.resize(bgr, (320, 180), interpolation=cv2.INTER_AREA)
+        frames.append(np.ascontiguousarray(small[:, :, ::-1].transpose(2, 0, 1)))      # RGB, CHW, uint8
+    frames = np.stack(frames)
+    stdv1 = 1.0 / math.sqrt(5 * 5 * 3)
+    w1 = rng.uniform(-stdv1, stdv1, (8, 3, 5, 5)).astype(np.float32)
+    b1 = rng.uniform(-stdv1, stdv1, 8).astype(np.float32)
+    conn = np.array([[f + 1, o + 1] for o in range(10) for f in sorted(rng.permutation(8)[:4])], np.int32)
+    stdv2 = 1.0 / math.sqrt(16 * 16 * 4)
+    w2 = rng.uniform(-stdv2, stdv2, (40, 16, 16)).astype(np.float32)
+    b2 = rng.uniform(-stdv2, stdv2, 10).astype(np.float32)
+    layers = [dict(weight=w1, bias=b1, tanh=True), dict(weight=w2, bias=b2, conn=conn)]
+    img = frames.astype(np.float32) / 255.0
+    f1 = O.filter_forward(img[0], layers)                         # 10 x 161 x 301
+    f2 = O.filter_forward(img[1], layers)
+    maxh = maxw = 17
+    in1 = np.ascontiguousarray(f1[:, 8:8 + 161 - 16, 8:8 + 301 - 16])   # prepareInput's crop
+    vol = O.spatial_matching(in1, f2, maxh, maxw)
+    prob = O.neg_softmax(vol)
+    K = maxh * maxw
+    idx, pmax = O.argmax_tie(prob, K, 8 * 17 + 9)
+    np.savez_compressed(os.path.join(HERE, "oracle_c1_cars.npz"), frames=frames, w1=w1, b1=b1, conn=conn, w2=w2,
+                        b2=b2, index=idx.reshape(145, 285).astype(np.int16),
+                        pmax_sample=pmax.reshape(145, 285)[::4, ::4].copy(),
+                        near_tie=np.packbits(O.top2_relgap(prob, K).reshape(145, 285) < 1e-5),
+                        feat2_sample=f2[:, ::20, ::20].copy())
+
+
 def main():
     assert O.ref() is not None, "build oracle/_ref first (make -C oracle)"
+    if "--cars-only" in sys.argv:
+        c1_cars_vectors()
+        return
     if "--calibration-only" in sys.argv:
         calibration_vectors()
         return
@@ -82,6 +124,7 @@ def main():
         return
     inline_vectors()
     calibration_vectors()
+    c1_cars_vectors()
     rng = np.random.default_rng(20261018)
 
     # ---- reference native code: extractOutput / extractOutputMarginalized

@@ -150,3 +150,48 @@ def test_cuda_cascade_radial_polar_match_oracle_vectors(dm):
     np.testing.assert_array_equal(dm.cartesian2polar(z["img"], z["c2p"]), z["polar"])
     lp, wIn = int(z["geom"][4]), int(z["geom"][3])
     np.testing.assert_array_equal(dm.cartesian2polar(z["polar"][:, :, lp:lp + wIn], z["p2c"]), z["back"])
+
+
+def _c1_cars(z):
+    layers = [dict(weight=z["w1"], bias=z["b1"], tanh=True), dict(weight=z["w2"], bias=z["b2"], conn=z["conn"])]
+    img = z["frames"].astype(np.float32) / 255.0
+    tie = np.unpackbits(z["near_tie"])[:145 * 285].reshape(145, 285).astype(bool)
+    return layers, img, tie
+
+
+def test_oracle_config1_car_frames(oracle):
+    """BASELINE config 1 (the reference's celiu/car1.jpg, car2.jpg pair at 320x180, default filter,
+    17x17 window): the oracle reproduces its committed flow indices and feature samples."""
+    z = load("oracle_c1_cars.npz")
+    layers, img, tie = _c1_cars(z)
+    f2 = oracle.filter_forward(img[1], layers)
+    np.testing.assert_allclose(f2[:, ::20, ::20], z["feat2_sample"], rtol=1e-6, atol=1e-7)
+    f1 = oracle.filter_forward(img[0], layers)
+    in1 = np.ascontiguousarray(f1[:, 8:8 + 145, 8:8 + 285])
+    prob = oracle.neg_softmax(oracle.spatial_matching(in1, f2, 17, 17))
+    idx, pmax = oracle.argmax_tie(prob, 289, 8 * 17 + 9)
+    assert ((idx.reshape(145, 285) != z["index"]) & ~tie).sum() == 0
+    np.testing.assert_allclose(pmax.reshape(145, 285)[::4, ::4], z["pmax_sample"], rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_config1_car_frames_from_raw_frames(dm):
+    """Config 1 end to end on the GPU: uint8 frames -> getFilter's two layers -> prepareInput ->
+    fused matcher, against the committed oracle indices (near ties excluded)."""
+    z = load("oracle_c1_cars.npz")
+    layers, img, tie = _c1_cars(z)
+    g = dm.Geometry(layers=[[3, 5, 5, 8], [4, 16, 16, 10]], maxh=17, maxw=17, hImg=180, wImg=320)
+    flt = dm.getFilter(g, np.random.default_rng(0))
+    convs = [m for m in flt.modules if hasattr(m, "weight")]
+    convs[0].weight[...], convs[0].bias[...] = z["w1"], z["b1"]
+    convs[1].connTable = z["conn"].copy()
+    convs[1].weight[...], convs[1].bias[...] = z["w2"], z["b2"]
+    flt.reset_weights()
+    model = dm.getModel(g, True, False, fused=True, filter=flt)
+    out = model.forward(dm.prepareInput(g, img[0], img[1]))
+    got = np.asarray(out["index"])
+    assert got.shape == (145, 285)
+    # the features differ from the CPU's in the last bits (FMA order): allow what the 1e-5 rule allows
+    bad = (got != z["index"]) & ~tie
+    assert bad.mean() < 2e-3, bad.sum()
+    np.testing.assert_allclose(np.asarray(out["pmax"])[::4, ::4], z["pmax_sample"], rtol=2e-4)
