@@ -824,7 +824,7 @@ class _FilteredModel(_Module):
 
 def getModel(geometry, full_image=True, prefiltered=False, fused=False, filter=None, rng=None, ctx=None):
     if geometry.multiscale:
-        return getModelMultiscale(geometry, full_image, prefiltered, ctx=ctx)
+        return getModelMultiscale(geometry, full_image, prefiltered, filter=filter, rng=rng, ctx=ctx)
     matcher = DenseMatch(geometry, ctx=ctx) if fused else _MatchModel(geometry, ctx=ctx)
     if prefiltered:
         return matcher
@@ -1076,13 +1076,32 @@ class _MultiscaleModel(_Module):
         return self.output
 
 
-def getModelMultiscale(geometry, full_image=True, prefiltered=True, ctx=None):
+class _MultiscaleFromFrames(_Module):
+    """getModelMultiscale(geometry, full_image, prefiltered=false): the per-scale prefilter
+    (average, zero padding, shared filter -- multiscaleInputs) in front of the prefiltered model.
+    forward({frame1, frame2}), both [C,H,W] with H, W multiples of the largest ratio.  The border
+    handling of the reference's nnx SpatialPyramid (out of tree) is replaced by zero padding of
+    the frames, see multiscaleInputs."""
+
+    def __init__(self, geometry, filter, ctx=None):
+        self.geometry, self.filter, self.ctx = geometry, filter, ctx
+        self.inner = _MultiscaleModel(geometry, ctx=ctx)
+        self.output = None
+
+    def getWeights(self):
+        return self.filter.getWeights()
+
+    def updateOutput(self, inp):
+        self.output = self.inner.forward(multiscaleInputs(self.geometry, self.filter, inp[0], inp[1], ctx=self.ctx))
+        return self.output
+
+
+def getModelMultiscale(geometry, full_image=True, prefiltered=False, filter=None, rng=None, ctx=None):
     assert geometry.output_extraction_method in (None, "max")
-    if not prefiltered:
-        raise DepthMatchError(_lib.DM_ERR_UNSUPPORTED, "getModelMultiscale: pass prefiltered maps "
-                              "(getMultiscalePrefilter's output)")
     assert geometry.ratios[0] == 1
-    return _MultiscaleModel(geometry, ctx=ctx)
+    if prefiltered:
+        return _MultiscaleModel(geometry, ctx=ctx)
+    return _MultiscaleFromFrames(geometry, filter or getFilter(geometry, rng, ctx), ctx=ctx)
 
 
 # ------------------------------------------------------------------ radial

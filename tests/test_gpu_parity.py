@@ -916,6 +916,9 @@ def test_multiscale_from_raw_frames(dm, oracle):
     assert ((np.asarray(out["index"]).reshape(-1) != idx) & ~tie).sum() == 0 and tie.mean() < 0.05
     inner = (slice(20, 44), slice(24, 72))
     assert np.median(np.asarray(out["flow_y"])[inner]) == 4 and np.median(np.asarray(out["flow_x"])[inner]) == 4
+    # the same through getModelMultiscale(prefiltered=false)
+    out2 = dm.getModelMultiscale(g, True, False, filter=flt).forward([img1, img2])
+    np.testing.assert_array_equal(np.asarray(out2["index"]), np.asarray(out["index"]))
 
 
 def test_winner_take_all_only_path_equals_the_full_path(dm, oracle, monkeypatch):
