@@ -1093,9 +1093,13 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
 namespace dm {
 
 // statistics pass for the soft-max volume: per-pixel min and 1/sum, nothing else
-static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin, float *vinv) {
+static int launch_stats(Call &call, const Prepared &pr, bool exact, bool small, float *vmin, float *vinv) {
   dm_ctx *ctx = call.ctx;
   const SweepGeom &g = pr.g;
+  const int cfg_th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
+  const int cfg_nslot = small ? ExtractCfgSmall::kNSlot : ExtractCfg::kNSlot;
+  const int cfg_threads = small ? ExtractCfgSmall::kThreads : ExtractCfg::kThreads;
+  const int cfg_cthreads = small ? ExtractCfgSmall::kCThreads : ExtractCfg::kCThreads;
   ExtractParams P;
   memset(&P, 0, sizeof(P));
   P.g = g;
@@ -1107,14 +1111,14 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, float *vmin,
   set_middle(&P, g.maxw);
   P.min_ssd = vmin;
   P.pmax = vinv;
-  const size_t extra = kBarBytes + (size_t)ExtractCfg::kCThreads * kP * sizeof(unsigned);
-  DM_CHECK(fit_ring(ctx, &P.g, ExtractCfg::kTH, ExtractCfg::kNSlot, extra));
+  const size_t extra = kBarBytes + (size_t)cfg_cthreads * kP * sizeof(unsigned);
+  DM_CHECK(fit_ring(ctx, &P.g, cfg_th, cfg_nslot, extra));
   const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
-  const void *kfn = pick_extract(false, pr.CT, exact ? kExact : kFma, kEpiScores);
+  const void *kfn = pick_extract(small, pr.CT, exact ? kExact : kFma, kEpiScores);
   DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = grid_for(ctx, kfn, ExtractCfg::kThreads, smem, g.ntiles);
+  const int grid = grid_for(ctx, kfn, cfg_threads, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&pr.tmap, (void *)&P};
-  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(ExtractCfg::kThreads), args, smem, ctx->stream));
+  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(cfg_threads), args, smem, ctx->stream));
   count_launch(ctx);
   return DM_OK;
 }
@@ -1149,9 +1153,12 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     DM_CHECK(call.alloc(&s, npx * 2 * sizeof(float)));
     float *vmin = static_cast<float *>(s), *vinv = vmin + npx;
     Prepared ps = pr;  // the statistics sweep runs with the extraction kernel's tile height
-    ps.g.tiles_y = (g.H1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH;
+    const long long big_tiles = (long long)g.tiles_x * ((g.H1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH) * g.N;
+    const bool small = big_tiles < ctx->num_sms && !getenv("DM_NO_SMALL_TILES");  // e.g. the coarse scales
+    const int th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
+    ps.g.tiles_y = (g.H1 + th - 1) / th;
     ps.g.ntiles = ps.g.tiles_x * ps.g.tiles_y * g.N;
-    DM_CHECK(launch_stats(call, ps, exact, vmin, vinv));
+    DM_CHECK(launch_stats(call, ps, exact, small, vmin, vinv));
     P.vmin = vmin;
     P.vinv = vinv;
   }
