@@ -865,7 +865,8 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     int rf = call.finish();
     return rc != DM_OK ? rc : rf;
   }
-  // 15-row tiles leave most SMs idle on one small pair: switch to the 5-row configuration
+  // 15-row tiles leave most SMs idle on one small pair (fewer tiles than half the SMs): switch
+  // to the 5-row configuration
   const long long big_tiles = (long long)((in->w1 + kTW - 1) / kTW) * ((in->h1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH) *
                               in->n_pairs;
   const char *force = getenv("DM_SSD_FORM");  // "diff" / "dot": tuning and tests only
@@ -873,7 +874,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   // twin launch of the dot form would cost more than it saves
   const bool big = (double)in->h1 * in->w1 * in->n_pairs * maxh * maxw * in->channels >= 5.0e8 ||
                    (force && !strcmp(force, "dot"));
-  const bool small = big_tiles < ctx->num_sms && !big && !getenv("DM_NO_SMALL_TILES");
+  const bool small = 2 * big_tiles < ctx->num_sms && !big && !getenv("DM_NO_SMALL_TILES");
   const int cfg_th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
   const int cfg_nslot = small ? ExtractCfgSmall::kNSlot : ExtractCfg::kNSlot;
   const int cfg_threads = small ? ExtractCfgSmall::kThreads : ExtractCfg::kThreads;
@@ -1154,7 +1155,7 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     float *vmin = static_cast<float *>(s), *vinv = vmin + npx;
     Prepared ps = pr;  // the statistics sweep runs with the extraction kernel's tile height
     const long long big_tiles = (long long)g.tiles_x * ((g.H1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH) * g.N;
-    const bool small = big_tiles < ctx->num_sms && !getenv("DM_NO_SMALL_TILES");  // e.g. the coarse scales
+    const bool small = 2 * big_tiles < ctx->num_sms && !getenv("DM_NO_SMALL_TILES");  // e.g. the coarse scales
     const int th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
     ps.g.tiles_y = (g.H1 + th - 1) / th;
     ps.g.ntiles = ps.g.tiles_x * ps.g.tiles_y * g.N;
