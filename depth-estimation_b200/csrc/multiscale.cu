@@ -257,10 +257,12 @@ ring_argmax_kernel(ScaleMaps maps, const int *chain, int h, int w, int maxh, int
         offs[e][s] = (l < L && s < n) ? __ldg(chain + (size_t)l * n + s) : -1;
       }
   }
-  // a warp takes 32 consecutive pixels: one gather + shuffle reduction per pixel, then every
-  // lane decodes and stores the result of "its" pixel (coalesced 8-byte stores)
-  for (long long px0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32; px0 < npx;
-       px0 += (long long)gridDim.x * 8 * 32) {
+  // a warp takes kBatch consecutive pixels: one gather + shuffle reduction per pixel, then the
+  // first kBatch lanes decode and store the results (coalesced 8-byte stores).  Small batches keep
+  // the last wave of the grid short (a 640x360 frame is only ~2 batches of 32 per resident warp).
+  constexpr int kBatch = 8;
+  for (long long px0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kBatch; px0 < npx;
+       px0 += (long long)gridDim.x * 8 * kBatch) {
    long long mywin = 0;
    // per-scale offset of the window of pixel px0 + lane, computed by its lane (the divisions
    // run once per 32 pixels) and broadcast inside the loop
@@ -274,7 +276,7 @@ ring_argmax_kernel(ScaleMaps maps, const int *chain, int h, int w, int maxh, int
        myoff[s] = ((Yl / rs) * (w / rs) + (Xl / rs)) * K;
      }
    }
-   for (int j = 0; j < 32 && px0 + j < npx; ++j) {
+   for (int j = 0; j < kBatch && px0 + j < npx; ++j) {
     const long long px = px0 + j;
     const float *base[kMaxRatios];
     if (in_regs) {
@@ -348,7 +350,7 @@ ring_argmax_kernel(ScaleMaps maps, const int *chain, int h, int w, int maxh, int
     if (vmid == best) win = middle;  // opticalflow_model.lua:157-159 with yx2xMulti(0,0)
     if (lane == j) mywin = win;      // every lane holds the reduced values
    }
-   if (px0 + lane < npx) {
+   if (lane < kBatch && px0 + lane < npx) {
      long long oy = 0, ox = 0;
      decode_spec(R, maxh, maxw, mywin, &oy, &ox);
      if (index) index[px0 + lane] = mywin;
@@ -548,8 +550,8 @@ int dm_multiscale_extract(dm_ctx *ctx, const float *const *in1, const float *con
     if (rc == DM_OK) {
       // middle index = yx2xMulti(0, 0): zero flow lives in the scale-1 block
       const int middle = ((maxh + 1) / 2 - 1) * maxw + (maxw + 1) / 2;
-      long long blocks = (npx + 255) / 256;  // 8 warps x 32 pixels
-      const long long cap = (long long)ctx->num_sms * 16;
+      long long blocks = (npx + 63) / 64;  // 8 warps x 8 pixels per pass
+      const long long cap = (long long)ctx->num_sms * 3;  // 80 registers: three CTAs per SM
       if (blocks > cap) blocks = cap;
       ring_argmax_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(
           maps, static_cast<const int *>(tp), h, w, maxh, maxw, R, L, middle,
