@@ -347,29 +347,44 @@ match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 }
 
 // ---------------------------------------------------------------- exact threshold pass
-// sorting networks of the reference (extract_output.cpp:27-33, :35-61), same order
-__device__ __constant__ unsigned char kNet4[5][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}, {1, 2}};
-__device__ __constant__ unsigned char kNet8[19][2] = {
-    {0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {1, 2}, {5, 6},
-    {0, 4}, {3, 7}, {1, 5}, {2, 6}, {1, 4}, {3, 6}, {2, 4}, {3, 5}, {3, 4}};
+// sorting networks of the reference (extract_output.cpp:27-33, :35-61), same order; compare-
+// exchanges with compile-time indices keep the eight (value, position) pairs in registers
+#define DM_CX(a, b)                \
+  if (val[b] > val[a]) {           \
+    float t_ = val[a];             \
+    val[a] = val[b];               \
+    val[b] = t_;                   \
+    t_ = pos[a];                   \
+    pos[a] = pos[b];               \
+    pos[b] = t_;                   \
+  }
 
 // Sort `M` (value,pos) pairs descending with the reference's network, return the
 // reference's ret and score (prefix sums in fp32, total in double).
-__device__ inline void net_sort_score(float *val, float *pos, int M, long long *ret, float *score) {
-  const int nex = M == 4 ? 5 : 19;
-  for (int e = 0; e < nex; ++e) {
-    const int a = M == 4 ? kNet4[e][0] : kNet8[e][0];
-    const int b = M == 4 ? kNet4[e][1] : kNet8[e][1];
-    if (val[b] > val[a]) {
-      float t = val[a]; val[a] = val[b]; val[b] = t;
-      t = pos[a]; pos[a] = pos[b]; pos[b] = t;
-    }
+template <int M>
+__device__ __forceinline__ void net_sort_score_m(float (&val)[8], float (&pos)[8], long long *ret, float *score) {
+  if (M == 4) {
+    DM_CX(0, 2) DM_CX(1, 3) DM_CX(0, 1) DM_CX(2, 3) DM_CX(1, 2)
+  } else {
+    DM_CX(0, 1) DM_CX(2, 3) DM_CX(4, 5) DM_CX(6, 7) DM_CX(0, 2) DM_CX(1, 3) DM_CX(4, 6) DM_CX(5, 7) DM_CX(1, 2)
+    DM_CX(5, 6) DM_CX(0, 4) DM_CX(3, 7) DM_CX(1, 5) DM_CX(2, 6) DM_CX(1, 4) DM_CX(3, 6) DM_CX(2, 4) DM_CX(3, 5)
+    DM_CX(3, 4)
   }
   *ret = (long long)pos[0];
+#pragma unroll
   for (int k = 1; k < M; ++k) val[k] = __fadd_rn(val[k], val[k - 1]);
   double acc = 0.0;
+#pragma unroll
   for (int k = 0; k < M; ++k) acc += (double)val[k];
   *score = (float)acc;
+}
+#undef DM_CX
+__device__ __forceinline__ void net_sort_score(float (&val)[8], float (&pos)[8], int M, long long *ret,
+                                               float *score) {
+  if (M == 4)
+    net_sort_score_m<4>(val, pos, ret, score);
+  else
+    net_sort_score_m<8>(val, pos, ret, score);
 }
 
 struct ThresholdPass {
