@@ -22,6 +22,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "match_kernels.cuh"
 
 namespace dm {
@@ -406,6 +408,7 @@ struct ThresholdPass {
 // pixel's shortlist of (dy, dx-block)s in scan order, recomputes those SSDs with the sweep's
 // arithmetic (all channel loads of a block issued before the first use, so a block costs one
 // memory latency), and applies extract_output.cpp:63-155 literally.
+template <int CT>
 __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPass T) {
   const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
   const unsigned gmask = 0xffu << (8 * grp);
@@ -419,9 +422,9 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
     const float *a = T.in1 + pn * T.s1n + y * T.s1y + x;
     const float *b0 = T.in2 + pn * T.s2n + y * T.s2y + x;
     const float m = T.vmin[px], inv = T.vinv[px];
-    float av[kMaxC];
+    float av[CT];
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) av[c] = c < T.C ? __ldg(a + c * T.s1c) : 0.0f;
+    for (int c = 0; c < CT; ++c) av[c] = c < T.C ? __ldg(a + c * T.s1c) : 0.0f;
     float val[8], pos[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) val[j] = pos[j] = 0.0f;
@@ -439,12 +442,12 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
         float pk = 0.0f;
         if (valid) {
           const float *b = b0 + dy * T.s2y + dxb + gl;
-          float bv[kMaxC];
+          float bv[CT];
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c) bv[c] = c < T.C ? __ldg(b + c * T.s2c) : 0.0f;
+          for (int c = 0; c < CT; ++c) bv[c] = c < T.C ? __ldg(b + c * T.s2c) : 0.0f;
           float acc = 0.0f;
 #pragma unroll
-          for (int c = 0; c < kMaxC; ++c)
+          for (int c = 0; c < CT; ++c)
             if (c < T.C) {
               const float d = av[c] - bv[c];
               acc = T.exact ? __fadd_rn(acc, __fmul_rn(d, d)) : fmaf(d, d, acc);
@@ -1036,14 +1039,24 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     T.todo = P.todo; T.todo_mask = P.todo_mask; T.ntodo = P.ntodo;
     T.vmin = P.vmin; T.vinv = P.vinv;
     T.index_thr = P.index_thr; T.score_thr = P.score_thr; T.n_untouched = P.n_untouched;
-    threshold_exact_kernel<<<ctx->num_sms * 12, 128, 0, ctx->stream>>>(T);
+    if (pr.CT == 4)
+      threshold_exact_kernel<4><<<ctx->num_sms * 12, 128, 0, ctx->stream>>>(T);
+    else if (pr.CT == 10)
+      threshold_exact_kernel<10><<<ctx->num_sms * 12, 128, 0, ctx->stream>>>(T);
+    else
+      threshold_exact_kernel<16><<<ctx->num_sms * 12, 128, 0, ctx->stream>>>(T);
     DM_CUDA(cudaGetLastError());
     count_launch(ctx);
     if (getenv("DM_DEBUG_TODO")) {  // diagnostics: how many pixels needed the exact pass
       unsigned n = 0;
       cudaMemcpyAsync(&n, P.ntodo, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream);
       cudaStreamSynchronize(ctx->stream);
-      fprintf(stderr, "[depthmatch] exact pass: %u of %zu pixels\n", n, npx);
+      std::vector<unsigned> hm((size_t)n * P.nwords);
+      cudaMemcpy(hm.data(), P.todo_mask, hm.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
+      unsigned long long bits = 0;
+      for (unsigned v : hm) bits += (unsigned long long)__builtin_popcount(v);
+      fprintf(stderr, "[depthmatch] exact pass: %u of %zu pixels, %.1f shortlisted blocks per pixel\n", n, npx,
+              n ? (double)bits / n : 0.0);
     }
   }
   return call.finish();
