@@ -416,9 +416,9 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
   const int per_row = T.bs.per_row();
   const unsigned ngroups = gridDim.x * 16;
   for (unsigned e = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 + grp; e < n; e += ngroups) {
-    const long long px = T.todo[e];
-    const int x = (int)(px % T.W1), y = (int)((px / T.W1) % T.H1);
-    const int pn = (int)(px / ((long long)T.W1 * T.H1));
+    const int px = T.todo[e];  // the list holds 32-bit pixel indices: 32-bit divisions
+    const int row = px / T.W1;
+    const int x = px - row * T.W1, pn = row / T.H1, y = row - pn * T.H1;
     const float *a = T.in1 + pn * T.s1n + y * T.s1y + x;
     const float *b0 = T.in2 + pn * T.s2n + y * T.s2y + x;
     const float m = T.vmin[px], inv = T.vinv[px];
