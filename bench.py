@@ -391,6 +391,27 @@ def main():
         line["volume_mode"] = {"value": Bv / (vms / 1e3), "unit": "frame-pairs/s", "kernel_ms": vms,
                                "roofline": {"bound": "hbm", "achieved": va, "peak": hbm_gbs, "unit": "GB/s",
                                             "frac": va / hbm_gbs, "kernel": "match_volume_kernel<10>"}}
+        # the same with the Minus + SoftMax stages (what the reference's model:forward returns):
+        # statistics sweep + volume sweep, timed with CUDA events around the call
+        import ctypes
+        from depthmatch import _lib as dml
+        pv = dm.match_volume(v1, v2, MAXH, MAXW, softmax=True, ctx=ctx)   # also the output buffer below
+        pr_ = dml.dm_pair()
+        pr_.in1, pr_.in2 = v1.data_ptr(), v2.data_ptr()
+        pr_.n_pairs, pr_.channels, pr_.h1, pr_.w1, pr_.h2, pr_.w2 = Bv, C, H1, W1, H, W
+        pr_.in1_stride_n, pr_.in1_stride_c, pr_.in1_stride_y = v1.stride(0), v1.stride(1), v1.stride(2)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(3):
+            dm.api.check(ctx._lib.dm_match_volume(ctx.handle, ctypes.byref(pr_), MAXH, MAXW, dml.DM_VOLUME_NEG_SOFTMAX,
+                                                  ctypes.c_void_p(pv.data_ptr())))
+        ev[1].record()
+        torch.cuda.synchronize()
+        sms = ev[0].elapsed_time(ev[1]) / 3
+        del pv
+        line["volume_softmax_mode"] = {"value": Bv / (sms / 1e3), "unit": "frame-pairs/s", "ms": sms,
+                                       "hbm_frac": BYTES_VOLUME * Bv / (sms / 1e3) / 1e9 / hbm_gbs}
 
     if not args.no_volume:
         # flow only (index + canvas): no probability is asked for, so the kernel skips the soft-max
