@@ -813,6 +813,18 @@ static int fit_ring(dm_ctx *ctx, SweepGeom *g, int tile_rows, int max_slots, siz
   return DM_OK;
 }
 
+// Can the tiled sweep take this shape?  The slab row must fit a TMA box (256 elements) and the
+// ring needs tile_rows + 2 slots next to the epilogue's shared memory.  Otherwise the untiled
+// kernel (match_generic.cu) does the job, slowly but for any window.
+static bool tiled_fits(dm_ctx *ctx, int channels, int maxw, int tile_rows, size_t extra, bool with_norm_row) {
+  const int CT = channels <= 4 ? 4 : (channels <= 10 ? 10 : 16);
+  const int WB = slab_width(maxw);
+  if (WB > 256) return false;
+  size_t slab = (size_t)((CT * WB + 31) & ~31);
+  if (with_norm_row) slab += (size_t)((WB + 31) & ~31);
+  return (size_t)(tile_rows + 2) * slab * sizeof(float) + extra <= ctx->smem_optin;
+}
+
 static const void *pick_extract(bool small, int CT, int mode, int epi) {
 #define DM_PICK3(cfg, ct, md)                                                                   \
   (epi == kEpiSoft ? (const void *)match_extract_kernel<cfg, ct, md, kEpiSoft>                  \
@@ -877,8 +889,11 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     DM_REQUIRE(h_img >= in->h1 && w_img >= in->w1, "canvas %dx%d smaller than output %dx%d", h_img,
                w_img, in->h1, in->w1);
   Call call(ctx, defer);
-  if (in->channels > kMaxC) {
-    DM_REQUIRE(!out->conf_marginal, "dm_match_extract: conf_marginal is not available beyond %d channels", kMaxC);
+  // worst-case epilogue footprint of the 15-row configuration (6 shortlist words)
+  const size_t extra_max = kBarBytes + (size_t)7 * ExtractCfg::kCThreads * kP * sizeof(unsigned);
+  if (in->channels > kMaxC || !tiled_fits(ctx, in->channels, maxw, ExtractCfg::kTH, extra_max, false)) {
+    DM_REQUIRE(!out->conf_marginal, "dm_match_extract: conf_marginal is not available beyond %d channels or "
+                                    "for windows the tiled kernel cannot hold", kMaxC);
     int rc = generic_match_extract(call, in, maxh, maxw, flags, prob_threshold, h_img, w_img, out);
     int rf = call.finish();
     return rc != DM_OK ? rc : rf;
@@ -1163,7 +1178,10 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
   mode &= ~DM_VOLUME_EXACT;
   DM_REQUIRE(mode == DM_VOLUME_SSD || mode == DM_VOLUME_NEG_SOFTMAX, "dm_match_volume: bad mode %d",
              mode);
-  if (in->channels > kMaxC) return generic_match_volume(call, in, maxh, maxw, mode, exact, out);
+  if (in->channels > kMaxC ||
+      !tiled_fits(ctx, in->channels, maxw, ExtractCfg::kTH,
+                  kBarBytes + (size_t)VolumeCfg::kWarps * 2 * kStgPlane * sizeof(float), false))
+    return generic_match_volume(call, in, maxh, maxw, mode, exact, out);
   Prepared pr;
   DM_CHECK(prepare(call, in, maxh, maxw, VolumeCfg::kTH, &pr));
   const SweepGeom &g = pr.g;

@@ -1111,3 +1111,20 @@ def test_no_writes_outside_the_output_buffers(dm):
             torch.cuda.synchronize()
             assert bool((vb[:G] == -12345.5).all()) and bool((vb[G + numel:] == -12345.5).all()), ("volume", mode, n, c, h2, w2)
             assert not bool((vb[G:G + numel] == -12345.5).any())
+
+
+def test_windows_beyond_the_tiled_kernel_fall_back_to_the_untiled_one(dm, oracle):
+    """A 129-wide window does not fit a TMA box and a 16-channel 97x97 window does not fit the
+    shared-memory ring: the call still answers (untiled kernel), bit-exact in exact mode."""
+    rng = np.random.default_rng(111)
+    for (c, mh, mw, h1, w1) in [(2, 5, 129, 6, 9), (16, 97, 97, 4, 7)]:
+        in2 = rng.standard_normal((c, h1 + mh - 1, w1 + mw - 1)).astype(np.float32)
+        in1 = (in2[:, mh // 2:mh // 2 + h1, mw // 3:mw // 3 + w1] + 0.1 * rng.standard_normal((c, h1, w1))).astype(np.float32)
+        got = dm.match_extract(in1, in2, mh, mw, exact=True, want=("index", "min_ssd", "pmax"))
+        vol = oracle.spatial_matching(in1, in2, mh, mw).reshape(-1, mh * mw)
+        prob = oracle.neg_softmax(vol)
+        idx, pmax = oracle.argmax_tie(prob, mh * mw, (math.ceil(mh / 2) - 1) * mw + math.ceil(mw / 2))
+        np.testing.assert_array_equal(got["index"].reshape(-1), idx)
+        np.testing.assert_array_equal(got["min_ssd"].reshape(-1), vol.min(-1))
+        np.testing.assert_allclose(got["pmax"].reshape(-1), pmax, rtol=1e-4)
+        np.testing.assert_array_equal(dm.match_volume(in1, in2, mh, mw, exact=True).reshape(-1, mh * mw), vol)
