@@ -33,14 +33,17 @@ def _stale(target, deps):
 
 def _compile(src, verbose):
     obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+    log = obj + ".ptxas.log"   # per translation unit, so an incremental build keeps the others
     deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS]
-    if not _stale(obj, deps):
-        return obj, ""
+    if not _stale(obj, deps) and os.path.exists(log):
+        return obj, open(log).read()
     cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (src, p.stdout))
-    return obj, p.stdout
+    with open(log, "w") as f:
+        f.write("==== %s\n%s" % (src, p.stdout))
+    return obj, "==== %s\n%s" % (src, p.stdout)
 
 
 def build(force=False, verbose=False):

@@ -49,8 +49,24 @@ struct Arena {
 
 }  // namespace dm
 
+namespace dm {
+// Tuning / diagnostic switches.  Read from the environment ONCE, in dm_create (DM_SSD_FORM,
+// DM_NO_SMALL_TILES, DM_NO_PIPELINE, DM_PIPE_CHUNK, DM_VOLUME_DEBUG, DM_DEBUG_TODO, DM_CONV_TILE);
+// dm_set_option changes them on a live context.  None of them is needed for normal use.
+struct Options {
+  int ssd_form = 0;  // 0 auto, 1 difference form always, 2 dot form whatever the norms
+  bool no_small_tiles = false, no_pipeline = false, debug_todo = false;
+  int pipe_chunk = 0, volume_debug = 0;
+  int conv_tile = 0, conv_target = 0;
+  int sweep = 0;     // 0 auto; other values select a sweep variant (tuning)
+};
+}  // namespace dm
+
 struct dm_ctx {
   int device = 0;
+  dm::Options opt;
+  // device counters of the most recent dm_match_extract on this context (dm_last_counts)
+  const unsigned *last_nresc = nullptr, *last_ntodo = nullptr;
   int num_sms = 0;
   size_t smem_optin = 0;
   cudaStream_t own_stream = nullptr;
@@ -113,6 +129,32 @@ int encode_tensor_map_4d(CUtensorMap *map, const float *base, const uint64_t dim
                          const uint64_t strides_bytes[3], const uint32_t box[4]);
 
 constexpr float kLog2e = 1.4426950408889634f;
+
+// Parameters of the untiled one-warp-per-pixel kernels (match_generic.cu); the tiled sweep
+// fills one too for the pixels it hands over to generic_rescore.
+struct GenericParams {
+  const float *in1, *in2;
+  long long s1n, s1c, s1y, s2n, s2c, s2y;
+  int N, C, H1, W1, maxh, maxw;
+  unsigned flags;
+  double thr;
+  int M, middle, cy, cx, h_img, w_img, hoff, woff;
+  long long *index;
+  float *min_ssd, *pmax, *flow_full;
+  long long *index_thr;
+  float *score_thr, *soft_yx;
+  unsigned long long *n_untouched;
+  float *radial_flow;  // argmin - 1 as float
+
+  float *conf_marginal;  // getOutputConfidences2's confidence, see dm_extract_out
+  // volume
+  int mode;
+  float *vol;
+  // list mode (generic_rescore): only the pixels list[0 .. *nlist) are computed
+  const int *list;
+  const unsigned *nlist;
+};
+int generic_rescore(dm_ctx *ctx, GenericParams P, const int *list, const unsigned *nlist);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device PTX

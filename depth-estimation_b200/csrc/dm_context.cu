@@ -1,6 +1,7 @@
 // dm_context.cu -- context, error reporting, pointer classification and staging.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dm_common.cuh"
@@ -182,9 +183,73 @@ int encode_tensor_map_4d(CUtensorMap *map, const float *base, const uint64_t dim
 
 using namespace dm;
 
+static int apply_option(Options *o, const char *name, const char *value) {
+  const int iv = value ? atoi(value) : 0;
+  if (!strcmp(name, "ssd_form")) {
+    if (!value || !*value || !strcmp(value, "auto")) o->ssd_form = 0;
+    else if (!strcmp(value, "diff")) o->ssd_form = 1;
+    else if (!strcmp(value, "dot")) o->ssd_form = 2;
+    else return DM_ERR_INVALID;
+  } else if (!strcmp(name, "no_small_tiles")) o->no_small_tiles = iv != 0;
+  else if (!strcmp(name, "no_pipeline")) o->no_pipeline = iv != 0;
+  else if (!strcmp(name, "debug_todo")) o->debug_todo = iv != 0;
+  else if (!strcmp(name, "pipe_chunk")) o->pipe_chunk = iv;
+  else if (!strcmp(name, "volume_debug")) o->volume_debug = iv;
+  else if (!strcmp(name, "sweep")) o->sweep = iv;
+  else if (!strcmp(name, "conv_tile")) {
+    o->conv_tile = o->conv_target = 0;
+    if (value) sscanf(value, "%d,%d", &o->conv_tile, &o->conv_target);
+  } else return DM_ERR_INVALID;
+  return DM_OK;
+}
+
+static void options_from_env(Options *o) {
+  static const char *const kEnv[][2] = {
+      {"DM_SSD_FORM", "ssd_form"},       {"DM_NO_SMALL_TILES", "no_small_tiles"}, {"DM_NO_PIPELINE", "no_pipeline"},
+      {"DM_DEBUG_TODO", "debug_todo"},   {"DM_PIPE_CHUNK", "pipe_chunk"},         {"DM_VOLUME_DEBUG", "volume_debug"},
+      {"DM_CONV_TILE", "conv_tile"},     {"DM_SWEEP", "sweep"}};
+  for (const auto &e : kEnv)
+    if (const char *v = getenv(e[0])) {
+      // flags set to the empty string or anything non-numeric count as "on"
+      const bool flag = !strcmp(e[1], "no_small_tiles") || !strcmp(e[1], "no_pipeline") || !strcmp(e[1], "debug_todo");
+      apply_option(o, e[1], flag && atoi(v) == 0 && strcmp(v, "0") ? "1" : v);
+    }
+}
+
 extern "C" {
 
 int dm_version(void) { return DM_VERSION; }
+
+int dm_set_option(dm_ctx *ctx, const char *name, const char *value) {
+  DM_REQUIRE(ctx && name, "dm_set_option: NULL argument");
+  const int rc = apply_option(&ctx->opt, name, value);
+  if (rc != DM_OK) set_error("dm_set_option: unknown option or value '%s' = '%s'", name, value ? value : "");
+  for (int i = 0; i < 2; ++i)
+    if (ctx->pipe[i]) ctx->pipe[i]->opt = ctx->opt;
+  return rc;
+}
+
+int dm_last_counts(dm_ctx *ctx, int64_t *rescored, int64_t *exact_pass) {
+  DM_REQUIRE(ctx != nullptr, "dm_last_counts: ctx is NULL");
+  DM_CUDA(cudaSetDevice(ctx->device));
+  DM_CUDA(cudaStreamSynchronize(ctx->stream));
+  unsigned v = 0;
+  if (rescored) {
+    *rescored = -1;
+    if (ctx->last_nresc) {
+      DM_CUDA(cudaMemcpy(&v, ctx->last_nresc, sizeof(v), cudaMemcpyDeviceToHost));
+      *rescored = v;
+    }
+  }
+  if (exact_pass) {
+    *exact_pass = -1;
+    if (ctx->last_ntodo) {
+      DM_CUDA(cudaMemcpy(&v, ctx->last_ntodo, sizeof(v), cudaMemcpyDeviceToHost));
+      *exact_pass = v;
+    }
+  }
+  return DM_OK;
+}
 
 const char *dm_last_error(void) { return dm::g_err; }
 
@@ -218,6 +283,7 @@ int dm_create(int device, dm_ctx **out) {
     return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
   }
   ctx->stream = ctx->own_stream;
+  options_from_env(&ctx->opt);
   *out = ctx;
   return DM_OK;
 }

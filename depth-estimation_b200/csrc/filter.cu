@@ -205,8 +205,8 @@ static int launch_layer(dm_ctx *ctx, const dm_filter::Layer &L, const float *in,
   double best = -1.0;
   int pick_tw = 0, pick_th = 0, pick_warps = 0, pick_group = 0;
   size_t pick_smem = 0, pick_tile = 0;
-  int force_tile = -1, force_target = 0;  // DM_CONV_TILE="<candidate 0-3>,<CTAs per SM 1-2>": tuning only
-  if (const char *f = getenv("DM_CONV_TILE")) sscanf(f, "%d,%d", &force_tile, &force_target);
+  // option conv_tile = "<candidate 0-3>,<CTAs per SM 1-2>": tuning only
+  const int force_target = ctx->opt.conv_target, force_tile = force_target ? ctx->opt.conv_tile : -1;
   for (int i = 0; i < 4; ++i) {
     for (int per_sm_target = 2; per_sm_target >= 1; --per_sm_target) {
       if (force_tile >= 0 && (i != force_tile || per_sm_target != force_target)) continue;

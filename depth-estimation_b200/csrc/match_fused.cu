@@ -59,6 +59,14 @@ struct ExtractParams {
   // found and only the one the bound selects runs (the other returns at once)
   const unsigned *stats;  // {max |a|^2, max |b|^2} as float bits; NULL: run unconditionally
   float dot_limit;        // kDot is taken when max |a|^2 + max |b|^2 <= dot_limit
+  // kDot: window entries closer than tau = tau_rel * (max |a|^2 + max |b|^2) to the running minimum
+  // cannot be ordered by the dot form (its absolute error is (C + 2) * 2^-24 of the norms, see
+  // dot_error_rel).  Such pixels -- and, in every form, pixels whose zero-flow entry is within a few
+  // ulp of the minimum -- are appended to `resc` and recomputed entry by entry in the difference
+  // form with the reference's literal order of operations (generic_rescore).
+  float tau_rel;
+  int *resc;
+  unsigned *nresc;
   const float *in2;       // frame 2 as the kernels address it, for the exact re-score of the winner
   long long s2n, s2c, s2y;
 };
@@ -89,12 +97,16 @@ struct ExtractEpi {
   // in reach of the threshold
   float e2[kP];
   int vfrom[kP];
+  unsigned amb;    // kDot: bit p = pixel p has a second entry within tau of its minimum
+  float tau;       // kDot: see ExtractParams::tau_rel; 0 otherwise
   unsigned *mask;  // [nwords][kP][kCThreads] words, this thread's column
   float *vmid;     // [kP][kCThreads]
 
   __device__ ExtractEpi(const ExtractParams &p, unsigned *smem_extra)
       : P(p), mask(smem_extra + threadIdx.x) {
     vmid = reinterpret_cast<float *>(smem_extra + (size_t)p.nwords * kP * kCThreads) + threadIdx.x;
+    tau = 0.0f;
+    if (DOT && p.stats) tau = p.tau_rel * (__uint_as_float(p.stats[0]) + __uint_as_float(p.stats[1]));
   }
 
   __device__ __forceinline__ void tile_begin(int, int, int) {
@@ -108,6 +120,7 @@ struct ExtractEpi {
       vfrom[p] = 0;
       vmid[p * kCThreads] = 0.0f;
     }
+    amb = 0u;
     for (int w = 0; w < P.nwords * kP; ++w) mask[w * kCThreads] = 0u;
   }
 
@@ -170,10 +183,11 @@ struct ExtractEpi {
       bm[p] = acc[p][0];
 #pragma unroll
       for (int r = 1; r < R; ++r) bm[p] = fminf(bm[p], acc[p][r]);
-      any |= bm[p] < m[p];
+      any |= (DOT ? bm[p] - tau : bm[p]) < m[p];
     }
     const int kbase = dy * P.g.maxw + dx0 + 1;  // 1-based index of (even pixel, r = 0)
-    if (any) {  // some pixel of this thread has a new running minimum in this block
+    if (any) {  // some pixel of this thread has a new running minimum in this block (kDot: or an
+                // entry the dot form cannot tell from the minimum)
 #pragma unroll
       for (int p = 0; p < kP; ++p)
         if (bm[p] < m[p]) {
@@ -181,7 +195,18 @@ struct ExtractEpi {
 #pragma unroll
           for (int r = R - 1; r >= 0; --r)
             if (acc[p][r] == bm[p]) rb = r;
+          if (DOT) {
+            // everything seen before is >= the old minimum: ambiguous iff that one is within tau;
+            // inside this block count the entries within tau of the new one
+            int near = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) near += acc[p][r] - tau <= bm[p] ? 1 : 0;
+            const bool a = m[p] - tau <= bm[p] || near > 1;
+            amb = (amb & ~(1u << p)) | (a ? 1u << p : 0u);
+          }
           new_min(p, bm[p], kbase - (p & 1) + rb, bit);
+        } else if (DOT && bm[p] - tau <= m[p]) {
+          amb |= 1u << p;
         }
     }
     if (WTA) return;
@@ -244,11 +269,14 @@ struct ExtractEpi {
     }
   }
 
-  // kDot: min_ssd is reported from the difference form (the dot form cancels: a perfect match
-  // would read a few ulp of |a|^2 + |b|^2 instead of 0).  a2 holds -2a.
+  // kDot: the winner is re-scored in the difference form (the dot form cancels: a perfect match
+  // would read a few ulp of |a|^2 + |b|^2 instead of 0) and the soft-max sums, which were taken
+  // relative to the dot-form minimum, are moved to the re-scored one: every term but the
+  // winner's own (exactly 1) scales by c = exp(m_diff - m_dot).  a2 holds -2a.
   template <int CT>
   __device__ __forceinline__ void tile_rescore(const float2 (&a2)[CT][2], int n, int y, int x0) {
-    if (!DOT || !P.min_ssd || y >= P.g.H1) return;
+    if (!DOT || y >= P.g.H1) return;
+    if (WTA && !P.min_ssd) return;
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
       if (x0 + p >= P.g.W1) continue;
@@ -262,9 +290,21 @@ struct ExtractEpi {
         const float d = a - (k < P.g.Cin ? __ldg(b + (long long)k * P.s2c) : 0.0f);
         acc = fmaf(d, d, acc);
       }
-      P.min_ssd[((size_t)n * P.g.H1 + y) * P.g.W1 + x0 + p] = acc;
+      if (!WTA) {
+        const float c = expf(acc - m[p]);
+        S[p] = fmaf(S[p] - 1.0f, c, 1.0f);
+        e2[p] *= c;
+        if (SOFT) {
+          const float rw = (float)(dy + 1), cw = (float)(dx + 1);
+          sy[p] = fmaf(sy[p] - rw, c, rw);
+          sx[p] = fmaf(sx[p] - cw, c, cw);
+        }
+      }
+      m[p] = acc;
     }
   }
+
+  __device__ __forceinline__ float idx_min_ssd(int p) const { return m[p]; }
 
   __device__ __forceinline__ void tile_end(int n, int y, int x0) {
     const SweepGeom &g = P.g;
@@ -277,12 +317,23 @@ struct ExtractEpi {
       const size_t o = ((size_t)n * g.H1 + y) * g.W1 + x;
       const float inv = WTA ? 1.0f : 1.0f / S[p];
       int win = idx[p];
-      if ((P.flags & DM_FLAG_TIE_MIDDLE) && win != P.middle) {
-        const float emid = expf(m[p] - vmid[p * kCThreads]);
-        if (emid * inv == inv) win = P.middle;  // p[middle] == max p (opticalflow_model.lua:157-159)
+      // Zero-flow tie rule, p[middle] == max p (opticalflow_model.lua:157-159), the same predicate in
+      // every epilogue: equal SSDs are a tie; an SSD a few ulp above the minimum may or may not
+      // round to the same probability, which only the reference's literal arithmetic decides --
+      // those pixels, like the ones the dot form could not order, go to the rescore list and
+      // every output of theirs is written by generic_rescore instead.
+      bool rescue = DOT && ((amb >> p) & 1u);
+      if (!DOT && (P.flags & DM_FLAG_TIE_MIDDLE) && win != P.middle) {
+        const float gapm = vmid[p * kCThreads] - idx_min_ssd(p);
+        if (gapm == 0.0f) win = P.middle;
+        else if (gapm < 1.0e-6f) rescue = true;
+      }
+      if (rescue && P.resc) {
+        P.resc[atomicAdd(P.nresc, 1u)] = (int)o;
+        continue;
       }
       if (P.index) P.index[o] = win;
-      if (P.min_ssd && !DOT) P.min_ssd[o] = m[p];  // kDot: written by tile_rescore
+      if (P.min_ssd) P.min_ssd[o] = m[p];
       if (P.pmax && !WTA) P.pmax[o] = inv;
       if (SOFT && P.conf_marginal) P.conf_marginal[o] = rowmax[p] * inv > P.p_thr ? 1.0f : 0.0f;
       if (SOFT && P.soft_yx) {
@@ -902,12 +953,12 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   // to the 5-row configuration
   const long long big_tiles = (long long)((in->w1 + kTW - 1) / kTW) * ((in->h1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH) *
                               in->n_pairs;
-  const char *force = getenv("DM_SSD_FORM");  // "diff" / "dot": tuning and tests only
+  const bool force_dot = ctx->opt.ssd_form == 2, force_diff = ctx->opt.ssd_form == 1;  // tuning and tests only
   // small calls (one 320x180 pair with a 17x17 window) are launch-bound: the norm pre-pass and the
   // twin launch of the dot form would cost more than it saves
   const bool big = (double)in->h1 * in->w1 * in->n_pairs * maxh * maxw * in->channels >= 5.0e8 ||
-                   (force && !strcmp(force, "dot"));
-  const bool small = 2 * big_tiles < ctx->num_sms && !big && !getenv("DM_NO_SMALL_TILES");
+                   force_dot;
+  const bool small = 2 * big_tiles < ctx->num_sms && !big && !ctx->opt.no_small_tiles;
   const int cfg_th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
   const int cfg_nslot = small ? ExtractCfgSmall::kNSlot : ExtractCfg::kNSlot;
   const int cfg_threads = small ? ExtractCfgSmall::kThreads : ExtractCfg::kThreads;
@@ -916,6 +967,8 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   DM_CHECK(prepare(call, in, maxh, maxw, cfg_th, &pr));
   const SweepGeom &g = pr.g;
   const size_t npx = (size_t)g.N * g.H1 * g.W1;
+  DM_REQUIRE(npx < ((size_t)1 << 31), "dm_match_extract: %zu output pixels in one call; the pixel lists are "
+                                      "32-bit, split the batch", npx);
 
   ExtractParams P;
   P.g = g;
@@ -987,6 +1040,15 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   const bool exact = flags & DM_FLAG_EXACT_SSD;
   P.stats = nullptr;
   P.dot_limit = 0.0f;
+  P.tau_rel = 0.0f;
+  {
+    // the rescore list (see ExtractParams::resc): worst case every pixel
+    void *scratch = nullptr;
+    DM_CHECK(call.alloc(&scratch, 256 + npx * sizeof(int)));
+    P.nresc = static_cast<unsigned *>(scratch);
+    P.resc = static_cast<int *>(scratch) + 64;
+    DM_CUDA(cudaMemsetAsync(P.nresc, 0, sizeof(unsigned), ctx->stream));
+  }
   P.in2 = pr.in2_dev;
   P.s2n = pr.s2n;
   P.s2c = pr.s2c;
@@ -1007,7 +1069,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   // is a few ulp of |a|^2 + |b|^2.  It is used when the largest norms keep that error under
   // ~1e-5 (the parity bar on the soft-max scores): a pre-pass writes |b|^2 per frame-2 pixel and
   // the maxima, then both kernels are launched and the device-side bound lets one of them run.
-  const bool allow_dot = big && !small && !exact && !(flags & DM_FLAG_DIFF_SSD) && !(force && !strcmp(force, "diff"));
+  const bool allow_dot = big && !small && !exact && !(flags & DM_FLAG_DIFF_SSD) && !force_diff;
   bool twin = false;
   ExtractParams Pd = P;
   CUtensorMap nbmap;
@@ -1035,7 +1097,15 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     const uint32_t box[4] = {(uint32_t)g.WB, 1u, 1u, 1u};
     DM_CHECK(encode_tensor_map_4d(&nbmap, static_cast<const float *>(nbuf), dims, strides, box));
     P.stats = Pd.stats = static_cast<const unsigned *>(stats);
-    P.dot_limit = Pd.dot_limit = (force && !strcmp(force, "dot")) ? 3.0e38f : 256.0f;
+    // Error model of the dot form: na, nb and the C products are each rounded once at a magnitude
+    // of at most |a|^2 + |b|^2, so |v_dot - v| <= e_rel * (|a|^2 + |b|^2) with e_rel = (C + 2) * 2^-24
+    // (a 4M-sample fp32 simulation at C = 10 peaks at 0.85 of that bound).  Scores: the soft-max
+    // sums move by the same relative amount, so the 1e-4 bar on scores allows norms up to
+    // 1e-4 / e_rel (140 for 10 channels).  Indices: entries closer than tau = 4 * e_rel * norms
+    // (twice the sum of two errors) to the minimum are not ordered here but in generic_rescore.
+    const float e_rel = (float)(pr.Cin + 2) * 5.9604645e-8f;
+    P.dot_limit = Pd.dot_limit = force_dot ? 3.0e38f : 1.0e-4f / e_rel;
+    Pd.tau_rel = 4.0f * e_rel;
     DM_CHECK(launch(Pd, nbmap, kDot));
     DM_CHECK(launch(P, pr.tmap, kFma));
     prof_end(ctx);
@@ -1043,6 +1113,23 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     prof_begin(ctx);
     DM_CHECK(launch(P, pr.tmap, exact ? kExact : kFma));
     prof_end(ctx);
+  }
+  {
+    GenericParams G;
+    memset(&G, 0, sizeof(G));
+    G.in1 = g.in1; G.s1n = g.s1n; G.s1c = g.s1c; G.s1y = g.s1y;
+    G.in2 = pr.in2_dev; G.s2n = pr.s2n; G.s2c = pr.s2c; G.s2y = pr.s2y;
+    G.N = g.N; G.C = pr.Cin; G.H1 = g.H1; G.W1 = g.W1; G.maxh = maxh; G.maxw = maxw;
+    G.flags = flags;
+    G.thr = prob_threshold;
+    G.M = P.M; G.middle = P.middle; G.cy = P.cy; G.cx = P.cx;
+    G.h_img = h_img; G.w_img = w_img; G.hoff = P.hoff; G.woff = P.woff;
+    G.index = P.index; G.min_ssd = P.min_ssd; G.pmax = P.pmax; G.flow_full = P.flow_full;
+    G.index_thr = P.index_thr; G.score_thr = P.score_thr; G.soft_yx = P.soft_yx;
+    G.n_untouched = P.n_untouched; G.conf_marginal = P.conf_marginal;
+    DM_CHECK(generic_rescore(ctx, G, P.resc, P.nresc));
+    ctx->last_nresc = P.nresc;
+    ctx->last_ntodo = P.ntodo;
   }
   if (want_thr) {
     ThresholdPass T;
@@ -1062,7 +1149,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
       threshold_exact_kernel<16><<<ctx->num_sms * 12, 128, 0, ctx->stream>>>(T);
     DM_CUDA(cudaGetLastError());
     count_launch(ctx);
-    if (getenv("DM_DEBUG_TODO")) {  // diagnostics: how many pixels needed the exact pass
+    if (ctx->opt.debug_todo) {  // diagnostics: how many pixels needed the exact pass
       unsigned n = 0;
       cudaMemcpyAsync(&n, P.ntodo, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream);
       cudaStreamSynchronize(ctx->stream);
@@ -1089,12 +1176,13 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
                        classify(in->in2) == PtrKind::Host;
   const int N = in->n_pairs;
   const bool async = (flags & DM_FLAG_ASYNC) != 0;  // the caller waits with dm_synchronize()
-  if (!host_in || N < 4 || ctx->is_child || getenv("DM_NO_PIPELINE"))
+  if (!host_in || N < 4 || ctx->is_child || ctx->opt.no_pipeline)
     return match_extract_impl(ctx, in, maxh, maxw, flags, prob_threshold, h_img, w_img, out, async);
   for (int i = 0; i < 2; ++i)
     if (!ctx->pipe[i]) {
       DM_CHECK(dm_create(ctx->device, &ctx->pipe[i]));
       ctx->pipe[i]->is_child = true;
+      ctx->pipe[i]->opt = ctx->opt;
     }
   const long long s1y = in->in1_stride_y ? in->in1_stride_y : in->w1;
   const long long s1c = in->in1_stride_c ? in->in1_stride_c : (long long)in->h1 * s1y;
@@ -1104,7 +1192,7 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
   const long long s2n = in->in2_stride_n ? in->in2_stride_n : (long long)in->channels * s2c;
   const size_t npx1 = (size_t)in->h1 * in->w1, canvas = (size_t)2 * h_img * w_img;
   int chunk = N >= 16 ? 4 : (N >= 8 ? 2 : 1);  // 4 north pairs = 3 full waves of tiles on 148 SMs
-  if (const char *e = getenv("DM_PIPE_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+  if (ctx->opt.pipe_chunk > 0) chunk = ctx->opt.pipe_chunk;
   int rc = DM_OK;
   for (int n0 = 0, c = 0; n0 < N && rc == DM_OK; n0 += chunk, ++c) {
     dm_pair sub = *in;
@@ -1194,14 +1282,14 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
   P.mode = mode;
   P.vmin = P.vinv = nullptr;
   P.out = static_cast<float *>(p);
-  P.debug = getenv("DM_VOLUME_DEBUG") ? atoi(getenv("DM_VOLUME_DEBUG")) : 0;
+  P.debug = ctx->opt.volume_debug;
   if (mode == DM_VOLUME_NEG_SOFTMAX) {
     void *s = nullptr;
     DM_CHECK(call.alloc(&s, npx * 2 * sizeof(float)));
     float *vmin = static_cast<float *>(s), *vinv = vmin + npx;
     Prepared ps = pr;  // the statistics sweep runs with the extraction kernel's tile height
     const long long big_tiles = (long long)g.tiles_x * ((g.H1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH) * g.N;
-    const bool small = 2 * big_tiles < ctx->num_sms && !getenv("DM_NO_SMALL_TILES");  // e.g. the coarse scales
+    const bool small = 2 * big_tiles < ctx->num_sms && !ctx->opt.no_small_tiles;  // e.g. the coarse scales
     const int th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
     ps.g.tiles_y = (g.H1 + th - 1) / th;
     ps.g.ntiles = ps.g.tiles_x * ps.g.tiles_y * g.N;

@@ -11,24 +11,6 @@ namespace dm {
 
 constexpr int kGWarps = 4;
 
-struct GenericParams {
-  const float *in1, *in2;
-  long long s1n, s1c, s1y, s2n, s2c, s2y;
-  int N, C, H1, W1, maxh, maxw;
-  unsigned flags;
-  double thr;
-  int M, middle, cy, cx, h_img, w_img, hoff, woff;
-  long long *index;
-  float *min_ssd, *pmax, *flow_full;
-  long long *index_thr;
-  float *score_thr, *soft_yx;
-  unsigned long long *n_untouched;
-  float *radial_flow;  // argmin - 1 as float
-
-  // volume
-  int mode;
-  float *vol;
-};
 
 __device__ __forceinline__ float ssd_at(const GenericParams &P, const float *a, const float *b,
                                         bool exact) {
@@ -51,8 +33,10 @@ __global__ void __launch_bounds__(kGWarps * 32) generic_kernel(const GenericPara
   const long long npx = (long long)P.N * P.H1 * P.W1;
   const int K = P.maxh * P.maxw;
   const bool exact = P.flags & DM_FLAG_EXACT_SSD;
-  for (long long px = (long long)blockIdx.x * kGWarps + (threadIdx.x >> 5); px < npx;
-       px += (long long)gridDim.x * kGWarps) {
+  const long long nwork = P.list ? (long long)*P.nlist : npx;
+  for (long long it = (long long)blockIdx.x * kGWarps + (threadIdx.x >> 5); it < nwork;
+       it += (long long)gridDim.x * kGWarps) {
+    const long long px = P.list ? (long long)P.list[it] : it;
     const int x = (int)(px % P.W1);
     const int y = (int)((px / P.W1) % P.H1);
     const int n = (int)(px / ((long long)P.W1 * P.H1));
@@ -128,7 +112,23 @@ __global__ void __launch_bounds__(kGWarps * 32) generic_kernel(const GenericPara
       sy += __shfl_xor_sync(0xffffffffu, sy, o);
       pmid = fmaxf(pmid, __shfl_xor_sync(0xffffffffu, pmid, o));
     }
+    float cmarg = 0.0f;
+    if (!VOLUME && P.conf_marginal) {
+      // opticalflow_model.lua:191-196: marginal over dx (TH sum: double accumulate, float result),
+      // then extractOutput(pm, thr) > 0, i.e. some row's marginal exceeds the threshold
+      for (int dy = 0; dy < P.maxh; ++dy) {
+        double rs = 0.0;
+        for (int dx = lane; dx < P.maxw; dx += 32) {
+          const float v = ssd_at(P, a, b0 + dy * P.s2y + dx, exact);
+          rs += (double)(float)((double)expf(vbest - v) * inv);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        if ((double)(float)rs > P.thr) cmarg = 1.0f;
+      }
+    }
     if (lane != 0) continue;
+    if (!VOLUME && P.conf_marginal) P.conf_marginal[px] = cmarg;
     int win = kbest + 1;
     if ((P.flags & DM_FLAG_TIE_MIDDLE) && pmid == pbest) win = P.middle;
     if (P.index) P.index[px] = win;
@@ -217,6 +217,19 @@ static int launch_generic(dm_ctx *ctx, const GenericParams &P, bool volume) {
     generic_kernel<true><<<(int)blocks, kGWarps * 32, 0, ctx->stream>>>(P);
   else
     generic_kernel<false><<<(int)blocks, kGWarps * 32, 0, ctx->stream>>>(P);
+  DM_CUDA(cudaGetLastError());
+  count_launch(ctx);
+  return DM_OK;
+}
+
+// The pixels the tiled sweep handed over (ExtractParams::resc): every requested output of theirs,
+// entry by entry in the reference's order of operations, SSD with separately rounded multiply
+// and add like the CPU path.  The list length is only known on the device.
+int generic_rescore(dm_ctx *ctx, GenericParams P, const int *list, const unsigned *nlist) {
+  P.list = list;
+  P.nlist = nlist;
+  P.flags |= DM_FLAG_EXACT_SSD;
+  generic_kernel<false><<<ctx->num_sms * 2, kGWarps * 32, 0, ctx->stream>>>(P);
   DM_CUDA(cudaGetLastError());
   count_launch(ctx);
   return DM_OK;

@@ -58,6 +58,8 @@ SIGNATURES = {
     "dm_launch_count": (_L, [_P]),
     "dm_set_profiling": (_I, [_P, _I]),
     "dm_last_kernel_ms": (_I, [_P, C.POINTER(_F)]),
+    "dm_set_option": (_I, [_P, C.c_char_p, C.c_char_p]),
+    "dm_last_counts": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "dm_match_volume": (_I, [_P, C.POINTER(dm_pair), _I, _I, _I, _P]),
     "dm_match_extract": (_I, [_P, C.POINTER(dm_pair), _I, _I, C.c_uint, _D, _I, _I,
                               C.POINTER(dm_extract_out)]),

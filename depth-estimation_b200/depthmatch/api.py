@@ -76,6 +76,17 @@ class Context:
         check(self._lib.dm_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def set_option(self, name, value):
+        """Tuning / diagnostic switch (dm_set_option): e.g. ("ssd_form", "dot" | "diff" | "auto")."""
+        check(self._lib.dm_set_option(self._h, str(name).encode(), str(value).encode()))
+
+    def last_counts(self):
+        """(pixels handed to the entry-by-entry rescore, pixels through the exact thresholded pass)
+        of the most recent match_extract on this context; synchronises."""
+        a, b = C.c_int64(-1), C.c_int64(-1)
+        check(self._lib.dm_last_counts(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def use_stream(self, cuda_stream):
         """cuda_stream: integer cudaStream_t (torch.cuda.current_stream().cuda_stream; 0 is the
         legacy default stream) or "own" for the context's private stream."""
@@ -154,7 +165,10 @@ def _pair_struct(args, in1, in2):
                 x = x.float()
             if x.dim() == 3:
                 x = x.unsqueeze(0)
-            if x.stride(-1) != 1 or any(s < 0 for s in x.stride()):
+            # dm_pair reads a stride of 0 as "contiguous default": broadcast / expanded views (stride 0
+            # over a dim of size > 1) are materialised instead of being misread as dense
+            if x.stride(-1) != 1 or any(s < 0 for s in x.stride()) or \
+                    any(s == 0 and n > 1 for s, n in zip(x.stride(), x.shape)):
                 x = x.contiguous()
             if x.is_cuda:
                 args.on_device = True
@@ -164,7 +178,8 @@ def _pair_struct(args, in1, in2):
                 x = x.astype(np.float32)
             if x.ndim == 3:
                 x = x[None]
-            if x.strides[-1] != x.itemsize or any(s < 0 for s in x.strides):
+            if x.strides[-1] != x.itemsize or any(s < 0 for s in x.strides) or \
+                    any(s == 0 and n > 1 for s, n in zip(x.strides, x.shape)):
                 x = np.ascontiguousarray(x)
         args.keep.append(x)
         return x
@@ -180,8 +195,17 @@ def _pair_struct(args, in1, in2):
     p.in1, p.in2 = pa, pb
     p.n_pairs, p.channels = int(a.shape[0]), int(a.shape[1])
     p.h1, p.w1, p.h2, p.w2 = int(a.shape[2]), int(a.shape[3]), int(b.shape[2]), int(b.shape[3])
-    p.in1_stride_n, p.in1_stride_c, p.in1_stride_y = sa[0] or 1, sa[1], sa[2]
-    p.in2_stride_n, p.in2_stride_c, p.in2_stride_y = sb[0] or 1, sb[1], sb[2]
+    # a size-1 dim may report any stride (0 included, which dm_pair reads as "default"): give it
+    # the stride a dense layout of the inner dims would have
+    def dense(st, shape):
+        st = list(st)
+        for d in (2, 1, 0):
+            if shape[d] == 1:
+                st[d] = st[d + 1] * int(shape[d + 1])
+        return st
+    sa, sb = dense(sa, a.shape), dense(sb, b.shape)
+    p.in1_stride_n, p.in1_stride_c, p.in1_stride_y = sa[0], sa[1], sa[2]
+    p.in2_stride_n, p.in2_stride_c, p.in2_stride_y = sb[0], sb[1], sb[2]
     return p, a, b
 
 

@@ -45,9 +45,31 @@ def band_inputs(in1, in2, band):
     return in1[..., y0:y1, :], in2[..., y0:hy1, :]
 
 
+def equal_row_bands(h1, world_size, maxh):
+    """Bands of EQUAL height hb = ceil(h1 / world) (the last ones may be cut or empty), so that the
+    per-band outputs are the rank-th hb-row slices of one [world*hb, ...] buffer and one in-place
+    all_gather_into_tensor assembles the full map with no staging copy.  Returns (hb, bands)."""
+    hb = (h1 + world_size - 1) // world_size
+    bands = []
+    for r in range(world_size):
+        y0, y1 = min(h1, r * hb), min(h1, (r + 1) * hb)
+        bands.append((y0, y1, y1 + maxh - 1 if y1 > y0 else y0))
+    return hb, bands
+
+
+def gather_bands_inplace(full, hb, rank, dist=None, async_op=False):
+    """The only collective of the path.  `full` is the preallocated [world*hb, ...] map (rows along
+    dim 0) whose slice [rank*hb, (rank+1)*hb) this rank has just written: one
+    all_gather_into_tensor, input aliasing its own slot of the output (NCCL's in-place form)."""
+    if dist is None:
+        import torch.distributed as dist
+    mine = full.narrow(0, rank * hb, hb)
+    return dist.all_gather_into_tensor(full, mine, async_op=async_op)
+
+
 def gather_bands(local, bands, dist=None, dim=0):
-    """all_gather per-band outputs (torch tensors, band rows along `dim`) into the full
-    map on every rank.  Bands may differ in height by one unit: pad to the tallest."""
+    """all_gather per-band outputs (torch tensors, band rows along `dim`) of UNEQUAL bands
+    (row_bands with an alignment) into the full map on every rank: pad to the tallest band."""
     import torch
     if dist is None:
         import torch.distributed as dist
@@ -62,14 +84,76 @@ def gather_bands(local, bands, dist=None, dim=0):
     return torch.cat([p.narrow(dim, 0, b[1] - b[0]) for p, b in zip(parts, bands)], dim=dim)
 
 
+class RowBandMatcher:
+    """BASELINE config 5: a stream of single large frame pairs, each cut in `world` equal row bands
+    (SURVEY 8e).  Per pair a rank runs the fused kernel on its band -- frame-1 rows [y0, y1),
+    frame-2 rows [y0, y1 + maxh - 1): the halo is re-read from the source, never exchanged -- with
+    the kernel writing straight into this rank's slice of the final maps, then the band outputs
+    are gathered in place on a side stream, so the gather of pair i overlaps the sweep of pair
+    i+1 (two result sets alternate).
+
+        m = RowBandMatcher(dm, h1, w1, maxh, maxw, rank, world, dist, want=("index", "pmax"))
+        h = m.step(in1, in2)      # torch CUDA tensors [C,H1,W1], [C,H2,W2], every rank holds them
+        maps = h.wait()           # {"index": [h1, w1], ...} on every rank
+    """
+
+    def __init__(self, dm, h1, w1, maxh, maxw, rank, world, dist=None, want=("index", "pmax"), ctx=None):
+        import torch
+        self.dm, self.maxh, self.maxw, self.rank, self.world, self.dist = dm, maxh, maxw, rank, world, dist
+        self.h1, self.w1, self.want = h1, w1, tuple(want)
+        self.hb, self.bands = equal_row_bands(h1, world, maxh)
+        dt = {"index": torch.int64, "index_thr": torch.int64}
+        self.full = [{k: torch.zeros((world * self.hb, w1), dtype=dt.get(k, torch.float32), device="cuda")
+                      for k in self.want} for _ in range(2)]
+        self.ctx = ctx
+        self.side = torch.cuda.Stream() if world > 1 else None
+        self.gathered = [None, None]   # event: the gather that last wrote result set i is complete
+        self.i = 0
+
+    class _Handle:
+        def __init__(self, maps, event, h1):
+            self.maps, self.event, self.h1 = maps, event, h1
+
+        def wait(self):
+            """Orders the caller's current stream after the gather and returns the full maps."""
+            import torch
+            if self.event is not None:
+                torch.cuda.current_stream().wait_event(self.event)
+            return {k: v[:self.h1] for k, v in self.maps.items()}
+
+    def step(self, in1, in2):
+        import torch
+        s = self.i & 1
+        self.i += 1
+        full = self.full[s]
+        cur = torch.cuda.current_stream()
+        if self.gathered[s] is not None:
+            cur.wait_event(self.gathered[s])   # the gather two steps ago still reads this set
+        y0, y1, hy1 = self.bands[self.rank]
+        if y1 > y0:
+            a, b = band_inputs(in1, in2, self.bands[self.rank])
+            out = {k: full[k][y0:y1].unsqueeze(0) for k in self.want}
+            self.dm.match_extract(a, b, self.maxh, self.maxw, want=self.want, out=out, ctx=self.ctx)
+        if self.world == 1:
+            return self._Handle(full, None, self.h1)
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(done)
+            for k in self.want:
+                gather_bands_inplace(full[k], self.hb, self.rank, self.dist)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.gathered[s] = ev
+        return self._Handle(full, ev, self.h1)
+
+
 def match_extract_row_bands(dm, in1, in2, maxh, maxw, rank, world_size, dist=None, **kw):
-    """Config-5 style execution of one large pair: this rank's band through the fused kernel,
-    then one all_gather of index / score maps.  in1/in2 are torch CUDA tensors [C,H,W]."""
-    bands = row_bands(in1.shape[-2], world_size, maxh)
-    a, b = band_inputs(in1, in2, bands[rank])
-    out = dm.match_extract(a, b, maxh, maxw, **kw)
-    return {k: gather_bands(v, bands, dist, dim=v.dim() - 2) for k, v in out.items()
-            if k not in ("n_untouched", "flow_full")}
+    """One large pair, one call (no pipelining): this rank's band through the fused kernel, then the
+    in-place gather.  in1/in2 are torch CUDA tensors [C,H,W]."""
+    want = tuple(k for k in kw.pop("want", ("index", "pmax")) if k not in ("n_untouched", "flow_full"))
+    m = RowBandMatcher(dm, in1.shape[-2], in1.shape[-1], maxh, maxw, rank, world_size, dist, want=want, **kw)
+    return m.step(in1, in2).wait()
 
 
 def _parse_cpulist(text):
@@ -104,3 +188,24 @@ def bind_to_gpu_numa_node(device=0):
         return node
     except (OSError, AttributeError, ValueError, RuntimeError):
         return None
+
+
+def numa_report(device=0):
+    """What the box exposes about the GPU's NUMA placement (why bind_to_gpu_numa_node may return
+    None): the sysfs numa_node of the GPU's PCI function (-1 = the hypervisor hides it) and the
+    number of NUMA nodes the OS sees."""
+    rep = {"gpu_numa_node_sysfs": None, "nodes_online": None}
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            rep["gpu_numa_node_sysfs"] = int(f.read().strip())
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        pass
+    try:
+        with open("/sys/devices/system/node/online") as f:
+            rep["nodes_online"] = f.read().strip()
+    except OSError:
+        pass
+    return rep

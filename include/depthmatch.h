@@ -65,6 +65,17 @@ int64_t dm_launch_count(dm_ctx *ctx);
  * make calls, read the duration of the most recent sweep kernel in milliseconds */
 int dm_set_profiling(dm_ctx *ctx, int on);
 int dm_last_kernel_ms(dm_ctx *ctx, float *ms);
+/* tuning / diagnostic switches (none is needed for normal use).  The environment variables
+ * DM_SSD_FORM, DM_NO_SMALL_TILES, DM_NO_PIPELINE, DM_PIPE_CHUNK, DM_VOLUME_DEBUG, DM_DEBUG_TODO,
+ * DM_CONV_TILE, DM_SWEEP are read once, in dm_create; this changes them on a live context.  Names:
+ * "ssd_form" = "auto" | "diff" | "dot"; "no_small_tiles", "no_pipeline", "debug_todo" = "0" | "1";
+ * "pipe_chunk", "volume_debug", "sweep" = integer; "conv_tile" = "<candidate>,<CTAs per SM>". */
+int dm_set_option(dm_ctx *ctx, const char *name, const char *value);
+/* the "near-tie pixels are logged" part of the parity contract: how many pixels of the most
+ * recent dm_match_extract on this context were handed to the entry-by-entry rescore (window entries
+ * the fast form could not order, zero-flow near-ties) and how many went through the exact
+ * thresholded-extraction pass.  Synchronises the context's stream.  -1 = not applicable. */
+int dm_last_counts(dm_ctx *ctx, int64_t *rescored, int64_t *exact_pass);
 
 /* ---- inputs ------------------------------------------------------------- */
 /* Two stacks of feature maps.  in1 is the (already window-cropped) frame-1 map

@@ -41,3 +41,15 @@ def dm():
     import depthmatch
     depthmatch.load()
     return depthmatch
+
+
+@pytest.fixture(autouse=True)
+def _reset_tuning_options(request):
+    """Tests that flip a tuning switch on the shared default context leave it in auto."""
+    yield
+    if "gpu" in request.keywords and _has_gpu():
+        import depthmatch
+        from depthmatch import api
+        for ctx in list(api._default.values()):
+            ctx.set_option("ssd_form", "auto")
+            ctx.set_option("no_small_tiles", "0")

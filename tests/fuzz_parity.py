@@ -25,12 +25,11 @@ for case in range(n_cases):
         in1[:, : in1.shape[1] // 2] = 0.5
         in2[:, : in2.shape[1] // 2] = 0.5
     K = maxh * maxw
-    os.environ.pop("DM_SSD_FORM", None)
-    os.environ.pop("DM_NO_SMALL_TILES", None)
-    if rng.random() < 0.5:   # small inputs take 5-row tiles by default: keep the 15-row kernels covered
-        os.environ["DM_NO_SMALL_TILES"] = "1"
-    if form in ("diff", "dot"):
-        os.environ["DM_SSD_FORM"] = form
+    ctx0 = dm.default_context()
+    # small inputs take 5-row tiles by default: keep the 15-row kernels covered
+    no_small = rng.random() < 0.5
+    ctx0.set_option("no_small_tiles", "1" if no_small else "0")
+    ctx0.set_option("ssd_form", form if form in ("diff", "dot") else "auto")
     want = ("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx")
     got = dm.match_extract(in1, in2, maxh, maxw, want=want, exact=(form == "exact"))
     wta = dm.match_extract(in1, in2, maxh, maxw, want=("index", "min_ssd"), exact=(form == "exact"))
@@ -79,7 +78,7 @@ for case in range(n_cases):
         errs.append("thr")
         if len(sys.argv) > 3:   # verbose: where and what
             badpx = np.argwhere((((got["index_thr"] != ret) & ~tie2) | ~np.isclose(got["score_thr"], sc, rtol=1e-4, atol=1e-6)) & ~near)
-            print("   small tiles off:", os.environ.get("DM_NO_SMALL_TILES"), "bad pixels", badpx[:6].tolist())
+            print("   small tiles off:", no_small, "bad pixels", badpx[:6].tolist())
             for (yy, xx) in badpx[:3]:
                 pr = prob.reshape(h1, w1, K)[yy, xx]
                 print("   px", yy, xx, "got", got["index_thr"][yy, xx], got["score_thr"][yy, xx], "want", ret[yy, xx], sc[yy, xx],

@@ -29,6 +29,15 @@ def _worker(rank, world, port, q):
         full = parallel.gather_bands(local, bands, dist, dim=0)
         want = torch.stack([in2[0, y:y + maxh].sum(0) + in1[1, y] for y in range(H1)])
         ok = bool(torch.equal(full, want))
+        # config-5 form: equal bands, the "kernel" writes its slice of the final map, in-place gather
+        hb, eb = parallel.equal_row_bands(H1, world, maxh)
+        final = torch.zeros((world * hb, W1))
+        y0, y1, hy1 = eb[rank]
+        a, b = parallel.band_inputs(in1, in2, eb[rank])
+        assert b.shape[1] == y1 - y0 + maxh - 1
+        final[y0:y1] = torch.stack([b[0, y:y + maxh].sum(0) + a[1, y] for y in range(y1 - y0)])
+        parallel.gather_bands_inplace(final, hb, rank, dist)
+        ok = ok and bool(torch.equal(final[:H1], want))
         mine = list(parallel.shard_pairs(7, world, rank))
         got = [None] * world
         dist.all_gather_object(got, mine)
@@ -66,6 +75,18 @@ def test_row_bands_cover_exactly(h1, world, maxh, align):
     for y0, y1, hy in bands:
         assert hy == (y1 + maxh - 1 if y1 > y0 else y0)
         assert y0 % align == 0
+
+
+@pytest.mark.parametrize("h1,world,maxh", [(1016, 8, 65), (328, 8, 33), (37, 2, 9), (5, 8, 3), (1016, 1, 65)])
+def test_equal_row_bands(h1, world, maxh):
+    sys.path.insert(0, os.path.join(ROOT, "depth-estimation_b200"))
+    from depthmatch import parallel
+    hb, bands = parallel.equal_row_bands(h1, world, maxh)
+    assert hb * world >= h1 and (hb - 1) * world < h1 and len(bands) == world
+    rows = [y for y0, y1, _ in bands for y in range(y0, y1)]
+    assert rows == list(range(h1))
+    for r, (y0, y1, hy) in enumerate(bands):
+        assert y0 == min(h1, r * hb) and y1 - y0 <= hb and hy == (y1 + maxh - 1 if y1 > y0 else y0)
 
 
 def test_shard_pairs_balanced():

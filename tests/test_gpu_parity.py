@@ -741,9 +741,9 @@ def test_async_host_call_and_cropped_view_equal_the_synchronous_call(dm):
 def test_dot_and_difference_forms_of_the_ssd_agree(dm, oracle, monkeypatch):
     """Large calls form the SSD as |a|^2+|b|^2-2a.b when the norms allow it (DM_FLAG_DIFF_SSD
     forces sum (a-b)^2).  Both must satisfy the parity bars against the oracle; min_ssd is
-    re-scored in the difference form; large norms fall back on the device.  DM_SSD_FORM=dot
+    re-scored in the difference form; large norms fall back on the device.  the ssd_form option
     forces the dot kernel on inputs small enough for the oracle."""
-    monkeypatch.setenv("DM_SSD_FORM", "dot")
+    dm.default_context().set_option("ssd_form", "dot")
     maxh, maxw = 9, 11
     in1, in2, _ = make_pair(10, 60, 90, maxh, maxw, seed=31, noise=0.3)
     K = maxh * maxw
@@ -776,7 +776,7 @@ def test_dot_and_difference_forms_of_the_ssd_agree(dm, oracle, monkeypatch):
     # automatic mode on a call large enough for the dot form: unit-variance features take it
     # (results differ from the difference form in the last bits), norms beyond the bound make the
     # device-side switch run the difference kernel, bit for bit
-    monkeypatch.delenv("DM_SSD_FORM")
+    dm.default_context().set_option("ssd_form", "auto")
     in1, in2, _ = make_pair(10, 260, 260, 33, 33, seed=32, noise=0.2)
     a = dm.match_extract(in1, in2, 33, 33, want=("index", "pmax"))
     b = dm.match_extract(in1, in2, 33, 33, want=("index", "pmax"), diff_form=True)
@@ -929,14 +929,14 @@ def test_winner_take_all_only_path_equals_the_full_path(dm, oracle, monkeypatch)
     in1[:, 10:20, 10:30] = 0.25          # a flat patch against a flat patch: ties -> zero flow
     in2[:, 10:26, 10:38] = 0.25
     for form in ("diff", "dot"):
-        monkeypatch.setenv("DM_SSD_FORM", form)
+        dm.default_context().set_option("ssd_form", form)
         full = dm.match_extract(in1, in2, maxh, maxw, canvas=(50, 70), want=("index", "min_ssd", "pmax"))
         wta = dm.match_extract(in1, in2, maxh, maxw, canvas=(50, 70), want=("index", "min_ssd"))
         np.testing.assert_array_equal(wta["index"], full["index"])
         np.testing.assert_array_equal(wta["min_ssd"], full["min_ssd"])
         np.testing.assert_array_equal(wta["flow_full"], full["flow_full"])
         assert (wta["index"][12:18, 12:28] == dm.getMiddleIndex(dm.Geometry(maxh=maxh, maxw=maxw))).all()
-    monkeypatch.delenv("DM_SSD_FORM")
+    dm.default_context().set_option("ssd_form", "auto")
     vol = oracle.spatial_matching(in1, in2, maxh, maxw).reshape(-1, maxh * maxw)
     prob = oracle.neg_softmax(vol)
     idx, _ = oracle.argmax_tie(prob, maxh * maxw, dm.getMiddleIndex(dm.Geometry(maxh=maxh, maxw=maxw)))
