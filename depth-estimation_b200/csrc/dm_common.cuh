@@ -66,7 +66,8 @@ struct dm_ctx {
   int device = 0;
   dm::Options opt;
   // device counters of the most recent dm_match_extract on this context (dm_last_counts)
-  const unsigned *last_nresc = nullptr, *last_ntodo = nullptr;
+  unsigned *counters = nullptr;  // [0] rescored, [1] exact pass; copied there on the stream after each call
+  bool counters_valid = false;
   int num_sms = 0;
   size_t smem_optin = 0;
   cudaStream_t own_stream = nullptr;

@@ -233,21 +233,10 @@ int dm_last_counts(dm_ctx *ctx, int64_t *rescored, int64_t *exact_pass) {
   DM_REQUIRE(ctx != nullptr, "dm_last_counts: ctx is NULL");
   DM_CUDA(cudaSetDevice(ctx->device));
   DM_CUDA(cudaStreamSynchronize(ctx->stream));
-  unsigned v = 0;
-  if (rescored) {
-    *rescored = -1;
-    if (ctx->last_nresc) {
-      DM_CUDA(cudaMemcpy(&v, ctx->last_nresc, sizeof(v), cudaMemcpyDeviceToHost));
-      *rescored = v;
-    }
-  }
-  if (exact_pass) {
-    *exact_pass = -1;
-    if (ctx->last_ntodo) {
-      DM_CUDA(cudaMemcpy(&v, ctx->last_ntodo, sizeof(v), cudaMemcpyDeviceToHost));
-      *exact_pass = v;
-    }
-  }
+  unsigned v[2] = {0, 0};
+  if (ctx->counters_valid) DM_CUDA(cudaMemcpy(v, ctx->counters, sizeof(v), cudaMemcpyDeviceToHost));
+  if (rescored) *rescored = ctx->counters_valid ? (int64_t)v[0] : -1;
+  if (exact_pass) *exact_pass = ctx->counters_valid ? (int64_t)v[1] : -1;
   return DM_OK;
 }
 
@@ -283,6 +272,12 @@ int dm_create(int device, dm_ctx **out) {
     return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
   }
   ctx->stream = ctx->own_stream;
+  e = cudaMalloc(&ctx->counters, 4 * sizeof(unsigned));
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+  }
   options_from_env(&ctx->opt);
   *out = ctx;
   return DM_OK;
@@ -295,6 +290,7 @@ int dm_destroy(dm_ctx *ctx) {
     if (ctx->pipe[i]) dm_destroy(ctx->pipe[i]);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
+  if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

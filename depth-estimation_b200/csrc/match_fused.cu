@@ -1128,8 +1128,6 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     G.index_thr = P.index_thr; G.score_thr = P.score_thr; G.soft_yx = P.soft_yx;
     G.n_untouched = P.n_untouched; G.conf_marginal = P.conf_marginal;
     DM_CHECK(generic_rescore(ctx, G, P.resc, P.nresc));
-    ctx->last_nresc = P.nresc;
-    ctx->last_ntodo = P.ntodo;
   }
   if (want_thr) {
     ThresholdPass T;
@@ -1161,6 +1159,13 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
               n ? (double)bits / n : 0.0);
     }
   }
+  // the counters of this call, for dm_last_counts (the scratch they live in is recycled)
+  DM_CUDA(cudaMemcpyAsync(ctx->counters, P.nresc, sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (P.ntodo)
+    DM_CUDA(cudaMemcpyAsync(ctx->counters + 1, P.ntodo, sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream));
+  else
+    DM_CUDA(cudaMemsetAsync(ctx->counters + 1, 0, sizeof(unsigned), ctx->stream));
+  ctx->counters_valid = true;
   return call.finish();
 }
 
