@@ -67,6 +67,8 @@ struct ExtractParams {
   float tau_rel;
   int *resc;
   unsigned *nresc;
+  const float *nb;        // |b|^2 per frame-2 pixel as the norm pre-pass wrote it (two-row sweep: tile end)
+  long long nb_sn, nb_sy;
   const float *in2;       // frame 2 as the kernels address it, for the exact re-score of the winner
   long long s2n, s2c, s2y;
 };
@@ -398,6 +400,10 @@ match_extract_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   ExtractEpi<Cfg, EPI, MODE == kDot> epi(P, extra);
   run_sweep<Cfg, CT, MODE>(&tmap, &tmap_nb, P.g, ring, full, epi);
 }
+
+}  // namespace dm
+#include "match_sweep2.cuh"
+namespace dm {
 
 // ---------------------------------------------------------------- exact threshold pass
 // sorting networks of the reference (extract_output.cpp:27-33, :35-61), same order; compare-
@@ -924,6 +930,35 @@ static int grid_for(dm_ctx *ctx, const void *kernel, int threads, size_t smem, i
   return ntiles < cap ? ntiles : cap;
 }
 
+using S2Cfg = Sweep2Cfg<7, 8>;
+
+// Launch of the two-row dot sweep.  DM_ERR_UNSUPPORTED (nothing launched, no error text) when the
+// ring does not fit next to the shortlist bitmap: the caller falls back to the one-row kernel.
+static int launch_sweep2(dm_ctx *ctx, const Prepared &pr, ExtractParams *Q, const CUtensorMap &nbmap) {
+  SweepGeom &g = Q->g;
+  g.tiles_y = (g.H1 + S2Cfg::kTH - 1) / S2Cfg::kTH;
+  g.ntiles = g.tiles_x * g.tiles_y * g.N;
+  const size_t extra = kBarBytes + (size_t)Q->nwords * S2Cfg::kPx * S2Cfg::kCThreads * sizeof(unsigned);
+  const size_t slab = (size_t)g.slab_floats * sizeof(float);
+  long long nslot = ((long long)ctx->smem_optin - (long long)extra) / (long long)slab;
+  if (nslot > S2Cfg::kNSlot) nslot = S2Cfg::kNSlot;
+  if (nslot < S2Cfg::kTH + 2) return DM_ERR_UNSUPPORTED;
+  g.nslot = (int)nslot;
+  const size_t smem = ring_bytes(g, g.nslot) + extra;
+  const bool wta = !Q->pmax && !Q->todo;
+  const void *kfn;
+  if (pr.CT == 4)
+    kfn = wta ? (const void *)match_sweep2_kernel<S2Cfg, 4, kEpiWta> : (const void *)match_sweep2_kernel<S2Cfg, 4, kEpiScores>;
+  else
+    kfn = wta ? (const void *)match_sweep2_kernel<S2Cfg, 10, kEpiWta> : (const void *)match_sweep2_kernel<S2Cfg, 10, kEpiScores>;
+  DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = g.ntiles < ctx->num_sms ? g.ntiles : ctx->num_sms;
+  void *args[] = {(void *)&pr.tmap, (void *)&nbmap, (void *)Q};
+  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(S2Cfg::kThreads), args, smem, ctx->stream));
+  count_launch(ctx);
+  return DM_OK;
+}
+
 }  // namespace dm
 
 using namespace dm;
@@ -1106,7 +1141,19 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     const float e_rel = (float)(pr.Cin + 2) * 5.9604645e-8f;
     P.dot_limit = Pd.dot_limit = force_dot ? 3.0e38f : 1.0e-4f / e_rel;
     Pd.tau_rel = 4.0f * e_rel;
-    DM_CHECK(launch(Pd, nbmap, kDot));
+    Pd.nb = static_cast<const float *>(nbuf);
+    Pd.nb_sn = (long long)g.H2 * w2p;
+    Pd.nb_sy = w2p;
+    // the dot leg: two output rows per warp (match_sweep2.cuh) when that kernel holds the shape,
+    // else the one-row sweep in its dot form
+    bool two_rows = false;
+    if (!Pd.soft_yx && pr.CT <= 10 && ctx->opt.sweep != 1) {
+      ExtractParams P2 = Pd;
+      int rc2 = launch_sweep2(ctx, pr, &P2, nbmap);
+      if (rc2 == DM_OK) two_rows = true;
+      else if (rc2 != DM_ERR_UNSUPPORTED) return rc2;
+    }
+    if (!two_rows) DM_CHECK(launch(Pd, nbmap, kDot));
     DM_CHECK(launch(P, pr.tmap, kFma));
     prof_end(ctx);
   } else {

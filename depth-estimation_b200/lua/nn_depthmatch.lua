@@ -96,24 +96,53 @@ end
 OutputExtractor.updateGradInput = nobackward('nn.OutputExtractor')
 
 -- ---------------------------------------------------------------- DenseMatch (fused)
--- forward({in1, in2}) returns the table processOutput would build (index, y, x, full, ...)
+-- forward({in1, in2}) returns the table processOutput(geometry, model:forward(input), true, nil)
+-- builds (opticalflow_model.lua:201-252), every field the callers read set:
+--   index, y, x, confidences, full (2 x hImg x wImg), full_confidences (hImg x wImg)
+-- for both extraction methods: 'max' (getOutputConfidences, :153-161: integer flow, confidences 1)
+-- and the default 'mean' (getOutputConfidences2, :171-199: soft means, marginal confidence).
 local DenseMatch, dparent = torch.class('nn.DenseMatch', 'nn.Module')
 function DenseMatch:__init(geometry)
    dparent.__init(self)
+   assert(not geometry.multiscale, 'nn.DenseMatch is the single-scale model; use dm_multiscale_extract')
    self.geometry = geometry
 end
 function DenseMatch:updateOutput(input)
    local g, in1, in2 = self.geometry, input[1], input[2]
    local h, w = in1:size(2), in1:size(3)
-   local ret = {index = torch.LongTensor(h, w), pmax = torch.Tensor(h, w),
-                index_thr = torch.LongTensor(h, w), scores = torch.Tensor(h, w),
-                soft = torch.Tensor(2, h, w), full = torch.Tensor(2, g.hImg, g.wImg)}
+   local use_max = g.output_extraction_method == 'max'
+   local ret = {index = torch.LongTensor(h, w), pmax = torch.Tensor(h, w)}
    local o = ffi.new('dm_extract_out')
    o.index, o.pmax = torch.data(ret.index), torch.data(ret.pmax)
-   o.index_thr, o.score_thr = torch.data(ret.index_thr), torch.data(ret.scores)
-   o.soft_yx, o.flow_full = torch.data(ret.soft), torch.data(ret.full)
+   local soft, marg
+   if use_max then
+      ret.full = torch.Tensor(2, g.hImg, g.wImg)
+      o.flow_full = torch.data(ret.full)
+   else
+      soft, marg = torch.Tensor(2, h, w), torch.Tensor(h, w)
+      o.soft_yx, o.conf_marginal = torch.data(soft), torch.data(marg)
+   end
    dm.check(C.dm_match_extract(ctx, dm.pair(in1, in2), g.maxh, g.maxw, dm.DM_FLAG_TIE_MIDDLE, 0.11,
                                g.hImg, g.wImg, o))
+   local yoffset, xoffset = math.ceil(g.maxh / 2), math.ceil(g.maxw / 2)   -- centered2onebased(geometry, 0, 0)
+   local hoffset, woffset = math.floor((g.hImg - h) / 2), math.floor((g.wImg - w) / 2)
+   if use_max then
+      -- the library pasted the integer flow (row - ceil(maxh/2), col - ceil(maxw/2)) into the canvas
+      ret.y = ret.full[1]:sub(1 + hoffset, h + hoffset, 1 + woffset, w + woffset):clone()
+      ret.x = ret.full[2]:sub(1 + hoffset, h + hoffset, 1 + woffset, w + woffset):clone()
+      ret.confidences = torch.Tensor(h, w):fill(1)
+   else
+      ret.y, ret.x = soft[1] - yoffset, soft[2] - xoffset
+      ret.confidences = marg
+      -- yx2x(geometry, floor(y + 0.5), floor(x + 0.5)) on the one-based soft means
+      local iy, ix = (soft[1] + 0.5):floor(), (soft[2] + 0.5):floor()
+      ret.index:copy((iy - 1) * g.maxw + ix)
+      ret.full = torch.Tensor(2, g.hImg, g.wImg):zero()
+      ret.full:sub(1, 1, 1 + hoffset, h + hoffset, 1 + woffset, w + woffset):copy(ret.y)
+      ret.full:sub(2, 2, 1 + hoffset, h + hoffset, 1 + woffset, w + woffset):copy(ret.x)
+   end
+   ret.full_confidences = torch.Tensor(g.hImg, g.wImg):zero()
+   ret.full_confidences:sub(1 + hoffset, h + hoffset, 1 + woffset, w + woffset):copy(ret.confidences)
    self.output = ret
    return ret
 end

@@ -33,6 +33,9 @@ for case in range(n_cases):
     want = ("index", "min_ssd", "pmax", "index_thr", "score_thr", "soft_yx")
     got = dm.match_extract(in1, in2, maxh, maxw, want=want, exact=(form == "exact"))
     wta = dm.match_extract(in1, in2, maxh, maxw, want=("index", "min_ssd"), exact=(form == "exact"))
+    # scores without the soft mean: in the dot form this is the two-rows-per-warp sweep
+    sco = dm.match_extract(in1, in2, maxh, maxw, want=("index", "min_ssd", "pmax", "index_thr", "score_thr"),
+                           exact=(form == "exact"))
     if rng.random() < 0.3:
         # the same pair inside a batch of host buffers (pipelined chunks) and as a strided crop view
         n = int(rng.integers(2, 7))
@@ -83,6 +86,16 @@ for case in range(n_cases):
                 pr = prob.reshape(h1, w1, K)[yy, xx]
                 print("   px", yy, xx, "got", got["index_thr"][yy, xx], got["score_thr"][yy, xx], "want", ret[yy, xx], sc[yy, xx],
                       "probs>0.1:", [(int(k) + 1, float(pr[k])) for k in np.nonzero(pr > 0.1)[0]])
+    if ((sco["index"].reshape(-1) != idx) & ~tie).any():
+        errs.append("scores index")
+    if not np.allclose(sco["pmax"].reshape(-1), pmax, rtol=1e-4):
+        errs.append("scores pmax")
+    if not np.allclose(sco["min_ssd"].reshape(-1)[~tie], mn[~tie], **tol) or \
+            not np.allclose(wta["min_ssd"].reshape(-1)[~tie], mn[~tie], **tol):
+        errs.append("scores/wta min_ssd")
+    if ((sco["index_thr"] != ret) & ~near & ~tie2).any() or \
+            not np.allclose(sco["score_thr"][~near], sc[~near], rtol=1e-4, atol=1e-6):
+        errs.append("scores thr")
     status = "ok" if not errs else "FAIL " + ",".join(errs)
     bad_total += bool(errs)
     print("case %2d C=%2d win=%2dx%2d in2=%3dx%3d form=%-5s noise=%.2f ties=%d: %s"

@@ -148,3 +148,57 @@ def test_lua_ffi_cdef_matches_the_header():
                  "dm_polar_remap", "dm_flow2depth", "dm_filter_create", "dm_filter_forward",
                  "dm_post_process_image", "dm_enlarge_mask", "dm_warp_homography"):
         assert name in l, name
+
+
+# ---------------------------------------------------------------------------------------------
+# The LuaJIT shims cannot be executed here (no Lua VM in the image).  tests/lua_check.py does what
+# is possible without one; the same checker accepts all 55 Lua files of the reference.
+# ---------------------------------------------------------------------------------------------
+LUA_DIR = os.path.join(ROOT, "depth-estimation_b200", "lua")
+
+
+@pytest.mark.parametrize("name", ["depthmatch_ffi.lua", "nn_depthmatch.lua", "depth_estimation_api_patch.lua"])
+def test_lua_shims_nest_and_close(name):
+    import lua_check
+    toks = lua_check.check_structure(open(os.path.join(LUA_DIR, name)).read())
+    assert len(toks) > 50
+    with pytest.raises(lua_check.LuaSyntaxError):       # the checker does reject broken files
+        lua_check.check_structure("function f(x) if x then return 1 end")
+
+
+def test_lua_c_calls_pass_the_headers_argument_counts():
+    import lua_check
+    protos = lua_check.header_arg_counts(open(os.path.join(ROOT, "include", "depthmatch.h")).read())
+    seen = set()
+    for name in os.listdir(LUA_DIR):
+        toks = lua_check.check_structure(open(os.path.join(LUA_DIR, name)).read())
+        for fn, nargs, line in lua_check.calls(toks, "C.dm_"):
+            assert fn[2:] in protos, "%s:%d calls %s, which the header does not declare" % (name, line, fn)
+            assert nargs == protos[fn[2:]], "%s:%d: %s called with %d arguments, the header has %d" % (
+                name, line, fn, nargs, protos[fn[2:]])
+            seen.add(fn[2:])
+    assert {"dm_match_extract", "dm_match_volume", "dm_extract_output", "dm_x2yx_multi", "dm_cascade_add"} <= seen
+
+
+def test_lua_api_patch_sets_every_field_the_reference_reads():
+    """depth_estimation_api.lua:171-182 reads poutput.full, poutput.y and poutput.full_confidences
+    right after the lines the patch replaces (full_confidences was nil -> mask:cmul raised).
+    Every field of processOutput's table must be assigned from the module's result, none to nil,
+    and nn.DenseMatch must assign each of them on both extraction methods."""
+    import lua_check
+    patch = lua_check.check_structure(open(os.path.join(LUA_DIR, "depth_estimation_api_patch.lua")).read())
+    fields = lua_check.table_fields(patch, "poutput")
+    assert fields is not None
+    for f in ("index", "y", "x", "confidences", "full", "full_confidences"):
+        assert f in fields and fields[f] != "nil", (f, fields)
+    mod = open(os.path.join(LUA_DIR, "nn_depthmatch.lua")).read()
+    body = mod[mod.index("function DenseMatch:updateOutput"):mod.index("DenseMatch.updateGradInput")]
+    for f in ("index", "y", "x", "confidences", "full", "full_confidences"):
+        assert re.search(r"ret\.%s\b[^=\n]*=[^=]" % f, body) or re.search(r"\b%s\s*=\s*torch\." % f, body), f
+    assert "conf_marginal" in body and "soft_yx" in body and "flow_full" in body
+    # the reference lines the patch relies on are still what they were
+    ref = os.path.join("/root/reference", "depth_estimation_api.lua")
+    if os.path.exists(ref):
+        lines = open(ref).read().split("\n")
+        assert "processOutput(geometry, moutput, true, nil)" in lines[167]
+        assert "poutput.full_confidences" in lines[181]
