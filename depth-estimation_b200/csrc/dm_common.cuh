@@ -66,6 +66,24 @@ struct dm_ctx {
   int device = 0;
   dm::Options opt;
   // device counters of the most recent dm_match_extract on this context (dm_last_counts)
+  // Launch plans: what a call computes once per (kernel, shape) instead of once per call -- the
+  // dynamic shared-memory attribute already granted to a kernel, occupancy answers, encoded tensor
+  // maps (keyed by base pointer + geometry; a steady-state caller passes the same buffers).
+  struct FuncPlan {
+    const void *fn;
+    int threads;
+    size_t smem;      // largest dynamic size granted so far
+    int per_sm;       // occupancy at (threads, smem_occ); 0 = not asked yet
+    size_t smem_occ;
+  };
+  std::vector<FuncPlan> func_plans;
+  struct MapPlan {
+    const void *base;
+    uint64_t dims[4], strides[3];
+    uint32_t box[4];
+    CUtensorMap map;
+  };
+  std::vector<MapPlan> map_plans;   // small, most recent first
   unsigned *counters = nullptr;  // [0] rescored, [1] exact pass; copied there on the stream after each call
   bool counters_valid = false;
   int num_sms = 0;
@@ -128,6 +146,13 @@ inline void prof_end(dm_ctx *ctx) {
 // library still loads on a box without a driver).
 int encode_tensor_map_4d(CUtensorMap *map, const float *base, const uint64_t dims[4],
                          const uint64_t strides_bytes[3], const uint32_t box[4]);
+// the same through the context's plan cache (dm_ctx::map_plans)
+int tensor_map_4d(dm_ctx *ctx, CUtensorMap *map, const float *base, const uint64_t dims[4],
+                  const uint64_t strides_bytes[3], const uint32_t box[4]);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the kernel needs more than it was granted
+int ensure_func_smem(dm_ctx *ctx, const void *fn, size_t smem);
+// resident CTAs per SM of (fn, threads, smem), asked from the runtime once
+int blocks_per_sm(dm_ctx *ctx, const void *fn, int threads, size_t smem);
 
 constexpr float kLog2e = 1.4426950408889634f;
 

@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
+
 #include "dm_common.cuh"
 
 namespace dm {
@@ -177,6 +179,59 @@ int encode_tensor_map_4d(CUtensorMap *map, const float *base, const uint64_t dim
     return DM_ERR_CUDA;
   }
   return DM_OK;
+}
+
+int tensor_map_4d(dm_ctx *ctx, CUtensorMap *map, const float *base, const uint64_t dims[4],
+                  const uint64_t strides_bytes[3], const uint32_t box[4]) {
+  for (size_t i = 0; i < ctx->map_plans.size(); ++i) {
+    const dm_ctx::MapPlan &p = ctx->map_plans[i];
+    if (p.base == base && !memcmp(p.dims, dims, sizeof(p.dims)) && !memcmp(p.strides, strides_bytes, sizeof(p.strides)) &&
+        !memcmp(p.box, box, sizeof(p.box))) {
+      *map = p.map;
+      if (i) std::swap(ctx->map_plans[i], ctx->map_plans[0]);
+      return DM_OK;
+    }
+  }
+  DM_CHECK(encode_tensor_map_4d(map, base, dims, strides_bytes, box));
+  dm_ctx::MapPlan p;
+  p.base = base;
+  memcpy(p.dims, dims, sizeof(p.dims));
+  memcpy(p.strides, strides_bytes, sizeof(p.strides));
+  memcpy(p.box, box, sizeof(p.box));
+  p.map = *map;
+  ctx->map_plans.insert(ctx->map_plans.begin(), p);
+  if (ctx->map_plans.size() > 16) ctx->map_plans.pop_back();
+  return DM_OK;
+}
+
+static dm_ctx::FuncPlan *func_plan(dm_ctx *ctx, const void *fn) {
+  for (auto &p : ctx->func_plans)
+    if (p.fn == fn) return &p;
+  ctx->func_plans.push_back({fn, 0, 0, 0, 0});
+  return &ctx->func_plans.back();
+}
+
+int ensure_func_smem(dm_ctx *ctx, const void *fn, size_t smem) {
+  dm_ctx::FuncPlan *p = func_plan(ctx, fn);
+  if (smem <= p->smem) return DM_OK;
+  DM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p->smem = smem;
+  return DM_OK;
+}
+
+int blocks_per_sm(dm_ctx *ctx, const void *fn, int threads, size_t smem) {
+  dm_ctx::FuncPlan *p = func_plan(ctx, fn);
+  if (p->per_sm > 0 && p->threads == threads && p->smem_occ == smem) return p->per_sm;
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  if (per_sm < 1) per_sm = 1;
+  p->per_sm = per_sm;
+  p->threads = threads;
+  p->smem_occ = smem;
+  return per_sm;
 }
 
 }  // namespace dm

@@ -832,7 +832,7 @@ static int prepare(Call &call, const dm_pair *in, int maxh, int maxw, int tile_r
   const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, (uint64_t)g.C, (uint64_t)g.N};
   const uint64_t strides[3] = {(uint64_t)s2y * 4, (uint64_t)s2c * 4, (uint64_t)s2n * 4};
   const uint32_t box[4] = {(uint32_t)g.WB, 1u, (uint32_t)out->CT, 1u};
-  DM_CHECK(encode_tensor_map_4d(&out->tmap, d2, dims, strides, box));
+  DM_CHECK(tensor_map_4d(ctx, &out->tmap, d2, dims, strides, box));
   // the kernels address the ring with the box's channel count; slots start on 128-byte
   // boundaries (TMA destination alignment)
   g.C = out->CT;
@@ -920,13 +920,7 @@ __global__ void norm_kernel(const float *in, long long sn, long long sc, long lo
 }
 
 static int grid_for(dm_ctx *ctx, const void *kernel, int threads, size_t smem, int ntiles) {
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) {
-    cudaGetLastError();
-    per_sm = 1;
-  }
-  if (per_sm < 1) per_sm = 1;
-  const int cap = ctx->num_sms * per_sm;
+  const int cap = ctx->num_sms * blocks_per_sm(ctx, kernel, threads, smem);
   return ntiles < cap ? ntiles : cap;
 }
 
@@ -951,7 +945,7 @@ static int launch_sweep2(dm_ctx *ctx, const Prepared &pr, ExtractParams *Q, cons
     kfn = wta ? (const void *)match_sweep2_kernel<S2Cfg, 4, kEpiWta> : (const void *)match_sweep2_kernel<S2Cfg, 4, kEpiScores>;
   else
     kfn = wta ? (const void *)match_sweep2_kernel<S2Cfg, 10, kEpiWta> : (const void *)match_sweep2_kernel<S2Cfg, 10, kEpiScores>;
-  DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DM_CHECK(ensure_func_smem(ctx, kfn, smem));
   const int grid = g.ntiles < ctx->num_sms ? g.ntiles : ctx->num_sms;
   void *args[] = {(void *)&pr.tmap, (void *)&nbmap, (void *)Q};
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(S2Cfg::kThreads), args, smem, ctx->stream));
@@ -1093,7 +1087,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     const size_t smem = ring_bytes(Q.g, Q.g.nslot) + extra;
     const bool wta = !Q.pmax && !Q.soft_yx && !Q.todo;  // index / flow / min_ssd only
     const void *kfn = pick_extract(small, pr.CT, mode, Q.soft_yx ? kEpiSoft : (wta ? kEpiWta : kEpiScores));
-    DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DM_CHECK(ensure_func_smem(ctx, kfn, smem));
     const int grid = grid_for(ctx, kfn, cfg_threads, smem, Q.g.ntiles);
     void *args[] = {(void *)&pr.tmap, (void *)&nbmap, (void *)&Q};
     DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(cfg_threads), args, smem, ctx->stream));
@@ -1130,7 +1124,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, 1u, (uint64_t)g.N};
     const uint64_t strides[3] = {(uint64_t)w2p * 4, (uint64_t)g.H2 * w2p * 4, (uint64_t)g.H2 * w2p * 4};
     const uint32_t box[4] = {(uint32_t)g.WB, 1u, 1u, 1u};
-    DM_CHECK(encode_tensor_map_4d(&nbmap, static_cast<const float *>(nbuf), dims, strides, box));
+    DM_CHECK(tensor_map_4d(ctx, &nbmap, static_cast<const float *>(nbuf), dims, strides, box));
     P.stats = Pd.stats = static_cast<const unsigned *>(stats);
     // Error model of the dot form: na, nb and the C products are each rounded once at a magnitude
     // of at most |a|^2 + |b|^2, so |v_dot - v| <= e_rel * (|a|^2 + |b|^2) with e_rel = (C + 2) * 2^-24
@@ -1144,10 +1138,12 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     Pd.nb = static_cast<const float *>(nbuf);
     Pd.nb_sn = (long long)g.H2 * w2p;
     Pd.nb_sy = w2p;
-    // the dot leg: two output rows per warp (match_sweep2.cuh) when that kernel holds the shape,
-    // else the one-row sweep in its dot form
+    // the dot leg: the one-row sweep in its dot form.  The two-rows-per-warp variant
+    // (match_sweep2.cuh, option sweep = 2) halves the shared-memory wavefronts per output but runs
+    // two warps per scheduler in lock-step phases; measured slower on B200, so it
+    // is opt-in.
     bool two_rows = false;
-    if (!Pd.soft_yx && pr.CT <= 10 && ctx->opt.sweep != 1) {
+    if (!Pd.soft_yx && pr.CT <= 10 && ctx->opt.sweep == 2) {
       ExtractParams P2 = Pd;
       int rc2 = launch_sweep2(ctx, pr, &P2, nbmap);
       if (rc2 == DM_OK) two_rows = true;
@@ -1299,7 +1295,7 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, bool small, 
   DM_CHECK(fit_ring(ctx, &P.g, cfg_th, cfg_nslot, extra));
   const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
   const void *kfn = pick_extract(small, pr.CT, exact ? kExact : kFma, kEpiScores);
-  DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DM_CHECK(ensure_func_smem(ctx, kfn, smem));
   const int grid = grid_for(ctx, kfn, cfg_threads, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&pr.tmap, (void *)&P};
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(cfg_threads), args, smem, ctx->stream));
@@ -1356,7 +1352,7 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
   (exact ? (const void *)match_volume_kernel<ct, true> : (const void *)match_volume_kernel<ct, false>)
   const void *kfn = pr.CT == 4 ? DM_PICKV(4) : (pr.CT == 10 ? DM_PICKV(10) : DM_PICKV(16));
 #undef DM_PICKV
-  DM_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DM_CHECK(ensure_func_smem(ctx, kfn, smem));
   const int grid = grid_for(ctx, kfn, VolumeCfg::kThreads, smem, g.ntiles);
   void *args[] = {(void *)&pr.tmap, (void *)&P};
   prof_begin(ctx);

@@ -20,6 +20,11 @@ BLOCKS = [
     ("p2c_mask", "radial/cartesian2polar.lua", 62, 85),          # getP2CMask buildMask
     ("flow2depth", "radial/radial_opticalflow_display.lua", 17, 52),
 ]
+# plain C++ function bodies (not inline.load strings): the lines strictly inside the braces
+CPP_BODIES = [
+    # ARdroneAPI::computeDepthMapFromFlow (signature on :99, closing brace on :140)
+    ("drone_depth", "ardrone/ardrone_api.cpp", 100, 139, "computeDepthMapFromFlow"),
+]
 
 
 def main():
@@ -32,6 +37,12 @@ def main():
         body = "\n".join(lines[a - 1:b]).replace("%%", "%")
         with open(os.path.join(out, name + ".inc"), "w") as f:
             f.write(body + "\n")
+    for name, rel, a, b, fn in CPP_BODIES:
+        lines = open(os.path.join(ref, rel), encoding="latin-1").read().split("\n")
+        assert fn in lines[a - 2] and lines[a - 2].rstrip().endswith("{") and lines[b].strip() == "}", (
+            name, lines[a - 2], lines[b])
+        with open(os.path.join(out, name + ".inc"), "w") as f:
+            f.write("\n".join(lines[a - 1:b]) + "\n")
 
 
 if __name__ == "__main__":

@@ -53,3 +53,4 @@ def _reset_tuning_options(request):
         for ctx in list(api._default.values()):
             ctx.set_option("ssd_form", "auto")
             ctx.set_option("no_small_tiles", "0")
+            ctx.set_option("sweep", "0")

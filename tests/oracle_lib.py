@@ -350,14 +350,20 @@ def radial_depth(flow, mh, mw, infty, which="oracle"):
     return ret, conf
 
 
-def depth_from_xflow(xflow, mask, m):
+def depth_from_xflow(xflow, mask, m, which="oracle"):
+    """computeDepthMapFromFlow (ardrone/ardrone_api.cpp:99-140); which="ref" runs the reference's own
+    statements compiled into oracle/_ref (depth is unspecified there where the confidence is 0)."""
     xflow, px = _f(xflow)
     mask, pm = _f(mask)
     h, w = xflow.shape
     depth = np.empty((h, w), np.float32)
     conf = np.empty((h, w), np.float32)
-    lib().orc_depth_from_xflow(px, pm, h, w, C.c_float(m), depth.ctypes.data_as(c_fp),
-                               conf.ctypes.data_as(c_fp))
+    if which == "oracle":
+        fn = lib().orc_depth_from_xflow
+    else:
+        assert ref() is not None, "oracle/_ref not built"
+        fn = ref().ref_depth_from_xflow
+    fn(px, pm, h, w, C.c_float(m), depth.ctypes.data_as(c_fp), conf.ctypes.data_as(c_fp))
     return depth, conf
 
 

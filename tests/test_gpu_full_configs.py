@@ -146,3 +146,32 @@ def test_hard_data_33x33_small_sizes_forced_dot(dm, oracle):
         assert_parity(rep, data)
         assert rep["rescored"] >= 7 * 40      # the flat block cannot be ordered by the dot form
         assert (got["index"][5:12, 20:60] == want["middle"]).all()
+
+
+@pytest.mark.parametrize("shape,data", [((10, 70, 190, 33, 33), "unrelated"), ((10, 100, 300, 17, 24), "0.3"),
+                                        ((4, 60, 140, 9, 9), "1.0"), ((10, 360, 640, 33, 33), "0.05")])
+def test_two_row_sweep_variant_vs_oracle(dm, oracle, shape, data):
+    """The opt-in two-rows-per-warp dot sweep (match_sweep2.cuh, option sweep = 2: measured slower than
+    the default on B200, kept as the record of that experiment) meets the same bars, on both of its
+    epilogues (scores and winner-take-all)."""
+    C, H, W, maxh, maxw = shape
+    ctx = dm.default_context()
+    ctx.set_option("sweep", "2")
+    ctx.set_option("ssd_form", "dot")
+    try:
+        in1, in2 = _pair(C, H, W, maxh, maxw, data, 91)
+        in1[:, 3:9, 10:40] = 0.25
+        in2[:, 3:9 + maxh - 1, 10:40 + maxw - 1] = 0.25       # a flat block: all-tie pixels go to the rescore
+        want = oracle_pair(oracle, in1, in2, maxh, maxw, canvas=(H, W))
+        got = dm.match_extract(in1, in2, maxh, maxw, canvas=(H, W), want=WANT)
+        rep = parity_report(got, want)
+        rep["rescored"] = ctx.last_counts()[0]
+        print("\n[parity] two-row sweep %r %s: %r" % (shape, data, rep))
+        assert_parity(rep, "two-row sweep scores")
+        assert rep["rescored"] >= 6 * 30
+        wta = dm.match_extract(in1, in2, maxh, maxw, canvas=(H, W), want=("index", "min_ssd"))
+        assert_parity(parity_report(wta, want), "two-row sweep wta")
+        np.testing.assert_array_equal(wta["index"], got["index"])
+    finally:
+        ctx.set_option("sweep", "0")
+        ctx.set_option("ssd_form", "auto")

@@ -114,3 +114,22 @@ def test_polar_luts_and_flow2depth_match_reference_inline_c(oracle):
     b = oracle.ref_flow2depth(flow, 20.3, 18.9, 55.5)
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("seed,shape", [(1, (24, 40)), (2, (7, 9)), (3, (36, 63))])
+def test_drone_depth_from_xflow_matches_reference_source(oracle, seed, shape):
+    """orc_depth_from_xflow against ARdroneAPI::computeDepthMapFromFlow compiled from
+    /root/reference/ardrone/ardrone_api.cpp:99-140 (behind a cv::Mat_<float> stand-in).  Flows stay in
+    the range the reference's 20-bin histogram can hold (rounded flow in [-8, 11])."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(seed)
+    h, w = shape
+    xflow = rng.uniform(-7.4, 10.4, (h, w)).astype(np.float32)
+    xflow[rng.random((h, w)) < 0.2] = 0.0
+    mask = (rng.random((h, w)) < 0.7).astype(np.float32)
+    mask[rng.random((h, w)) < 0.1] = 0.4          # non-zero but not confident
+    da, ca = oracle.depth_from_xflow(xflow, mask, 0.37, "oracle")
+    db, cb = oracle.depth_from_xflow(xflow, mask, 0.37, "ref")
+    np.testing.assert_array_equal(ca, cb)
+    np.testing.assert_array_equal(da[cb > 0], db[cb > 0])
+    assert (cb > 0).sum() > 10
