@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "dm_common.cuh"
+#include "filter_tc.cuh"
 
 struct dm_filter {
   struct Layer {
@@ -30,6 +31,8 @@ struct dm_filter {
     float *bias;    // [n_out]
     int *row_ptr;   // [n_out + 1]
     int *from;      // [n_conn]
+    dm::TcPlan tc;  // tensor-core path (filter_tc.cu): plan and packed hi / lo weight operands
+    float *tcB;
   };
   int device;
   std::vector<Layer> layers;
@@ -351,6 +354,19 @@ int dm_filter_create(dm_ctx *ctx, const dm_conv_layer *layers, int n_layers, dm_
     for (int o = 0; o < L.n_out; ++o) L.max_conn_per_out = std::max(L.max_conn_per_out, rp[o + 1] - rp[o]);
     if (L.max_conn_per_out < 1) L.max_conn_per_out = 1;
     prev_out = l.n_out;
+    L.tcB = nullptr;
+    if (dm::tc_plan_layer(ctx, l.n_in, l.n_out, l.kh, l.kw, &L.tc)) {
+      std::vector<float> packed;
+      dm::tc_pack_weights(L.tc, l.n_in, l.n_out, l.kh, l.kw, l.n_conn, l.conn, l.weight, &packed);
+      cudaError_t e2 = cudaMalloc(&L.tcB, packed.size() * sizeof(float));
+      if (e2 == cudaSuccess) e2 = cudaMemcpy(L.tcB, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice);
+      if (e2 != cudaSuccess) {
+        cudaGetLastError();
+        if (L.tcB) cudaFree(L.tcB);
+        L.tcB = nullptr;
+        L.tc.ok = 0;   // the CUDA-core kernel still serves the layer
+      }
+    }
     f->layers.push_back(L);
   }
   cudaError_t e = cudaMalloc(&f->blob, host.size());
@@ -375,6 +391,8 @@ int dm_filter_destroy(dm_filter *f) {
   if (!f) return DM_OK;
   cudaSetDevice(f->device);
   if (f->blob) cudaFree(f->blob);
+  for (auto &L : f->layers)
+    if (L.tcB) cudaFree(L.tcB);
   delete f;
   return DM_OK;
 }
@@ -425,7 +443,15 @@ int dm_filter_forward(dm_ctx *ctx, const dm_filter *f, const float *in, int n_im
       DM_CHECK(call.alloc(&tmp, (size_t)n_img * L.n_out * nh * nw * 4));
       dst = static_cast<float *>(tmp);
     }
-    DM_CHECK(launch_layer(ctx, L, cur, dst, n_img, ch, cw, pl, pr, pt, pb));
+    // option conv = 2: the tcgen05 tensor-core kernel (filter_tc.cu) where the layer fits it.  It is
+    // parity-green but measured slower than the CUDA-core kernel on B200 (three-term
+    // tf32 split, connection-table zeros and the per-row operand staging eat the tensor advantage on
+    // these 3..16-plane layers), so it is opt-in.
+    if (L.tc.ok && ctx->opt.conv == 2)
+      DM_CHECK(dm::tc_launch_layer(ctx, L.tc, L.tcB, L.bias, L.n_in, L.n_out, L.kh, L.kw, L.tanh_after, cur, dst, n_img,
+                                   ch, cw, pl, pr, pt, pb));
+    else
+      DM_CHECK(launch_layer(ctx, L, cur, dst, n_img, ch, cw, pl, pr, pt, pb));
     cur = dst;
     ch = nh;
     cw = nw;

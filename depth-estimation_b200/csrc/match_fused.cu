@@ -29,6 +29,7 @@
 namespace dm {
 
 constexpr int kBarBytes = 384;  // room for the 2*kNSlot mbarriers, keeps what follows 128-byte aligned
+constexpr int kBar2Bytes = 512; // two-row sweep: 2*kNSlot mbarriers + kNSlot refill counters
 
 struct ExtractParams {
   SweepGeom g;
@@ -67,6 +68,7 @@ struct ExtractParams {
   float tau_rel;
   int *resc;
   unsigned *nresc;
+  int dbg;                // tuning switches of the two-row sweep (option volume_debug): 1 = no epilogue
   const float *nb;        // |b|^2 per frame-2 pixel as the norm pre-pass wrote it (two-row sweep: tile end)
   long long nb_sn, nb_sy;
   const float *in2;       // frame 2 as the kernels address it, for the exact re-score of the winner
@@ -450,6 +452,7 @@ struct ThresholdPass {
   const float *in1, *in2;
   long long s1n, s1c, s1y, s2n, s2c, s2y;
   int N, C, H1, W1, maxh, maxw, nwords, gb, M, exact;
+  int mark;  // diagnostics (option debug_todo): score_thr = -1 on the pixels this pass handled
   BlockSchedule bs;
   double thr;
   const int *todo;
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(128) threshold_exact_kernel(const ThresholdPas
     else if (T.n_untouched)
       atomicAdd(T.n_untouched + pn, 1ull);
     if (T.index_thr) T.index_thr[px] = ret;
-    if (T.score_thr) T.score_thr[px] = score;
+    if (T.score_thr) T.score_thr[px] = T.mark ? -1.0f : score;
   }
 }
 
@@ -924,7 +927,7 @@ static int grid_for(dm_ctx *ctx, const void *kernel, int threads, size_t smem, i
   return ntiles < cap ? ntiles : cap;
 }
 
-using S2Cfg = Sweep2Cfg<7, 8>;
+using S2Cfg = Sweep2Cfg<8, 6>;
 
 // Launch of the two-row dot sweep.  DM_ERR_UNSUPPORTED (nothing launched, no error text) when the
 // ring does not fit next to the shortlist bitmap: the caller falls back to the one-row kernel.
@@ -932,7 +935,8 @@ static int launch_sweep2(dm_ctx *ctx, const Prepared &pr, ExtractParams *Q, cons
   SweepGeom &g = Q->g;
   g.tiles_y = (g.H1 + S2Cfg::kTH - 1) / S2Cfg::kTH;
   g.ntiles = g.tiles_x * g.tiles_y * g.N;
-  const size_t extra = kBarBytes + (size_t)Q->nwords * S2Cfg::kPx * S2Cfg::kCThreads * sizeof(unsigned);
+  if (Q->gb != 1) return DM_ERR_UNSUPPORTED;  // one shortlist bit per block only
+  const size_t extra = kBar2Bytes + (size_t)Q->nwords * S2Cfg::kPx * S2Cfg::kCThreads * sizeof(unsigned);
   const size_t slab = (size_t)g.slab_floats * sizeof(float);
   long long nslot = ((long long)ctx->smem_optin - (long long)extra) / (long long)slab;
   if (nslot > S2Cfg::kNSlot) nslot = S2Cfg::kNSlot;
@@ -940,11 +944,15 @@ static int launch_sweep2(dm_ctx *ctx, const Prepared &pr, ExtractParams *Q, cons
   g.nslot = (int)nslot;
   const size_t smem = ring_bytes(g, g.nslot) + extra;
   const bool wta = !Q->pmax && !Q->todo;
+  // straight-line row body for the benchmark's window class (four full blocks + a 2-wide tail)
+  const bool n8_4 = g.bs.n8 == 4 && g.bs.tail_r == 2 && ctx->opt.sweep != 3;
   const void *kfn;
+#define DM_PICK2(ct, epi) (n8_4 ? (const void *)match_sweep2_kernel<S2Cfg, ct, epi, 4> : (const void *)match_sweep2_kernel<S2Cfg, ct, epi, 0>)
   if (pr.CT == 4)
-    kfn = wta ? (const void *)match_sweep2_kernel<S2Cfg, 4, kEpiWta> : (const void *)match_sweep2_kernel<S2Cfg, 4, kEpiScores>;
+    kfn = wta ? DM_PICK2(4, kEpiWta) : DM_PICK2(4, kEpiScores);
   else
-    kfn = wta ? (const void *)match_sweep2_kernel<S2Cfg, 10, kEpiWta> : (const void *)match_sweep2_kernel<S2Cfg, 10, kEpiScores>;
+    kfn = wta ? DM_PICK2(10, kEpiWta) : DM_PICK2(10, kEpiScores);
+#undef DM_PICK2
   DM_CHECK(ensure_func_smem(ctx, kfn, smem));
   const int grid = g.ntiles < ctx->num_sms ? g.ntiles : ctx->num_sms;
   void *args[] = {(void *)&pr.tmap, (void *)&nbmap, (void *)Q};
@@ -1070,6 +1078,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
   P.stats = nullptr;
   P.dot_limit = 0.0f;
   P.tau_rel = 0.0f;
+  P.dbg = 0;
   {
     // the rescore list (see ExtractParams::resc): worst case every pixel
     void *scratch = nullptr;
@@ -1135,6 +1144,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     const float e_rel = (float)(pr.Cin + 2) * 5.9604645e-8f;
     P.dot_limit = Pd.dot_limit = force_dot ? 3.0e38f : 1.0e-4f / e_rel;
     Pd.tau_rel = 4.0f * e_rel;
+    Pd.dbg = ctx->opt.volume_debug;
     Pd.nb = static_cast<const float *>(nbuf);
     Pd.nb_sn = (long long)g.H2 * w2p;
     Pd.nb_sy = w2p;
@@ -1143,7 +1153,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     // two warps per scheduler in lock-step phases; measured slower on B200, so it
     // is opt-in.
     bool two_rows = false;
-    if (!Pd.soft_yx && pr.CT <= 10 && ctx->opt.sweep == 2) {
+    if (!Pd.soft_yx && pr.CT <= 10 && (ctx->opt.sweep == 2 || ctx->opt.sweep == 3)) {
       ExtractParams P2 = Pd;
       int rc2 = launch_sweep2(ctx, pr, &P2, nbmap);
       if (rc2 == DM_OK) two_rows = true;
@@ -1179,6 +1189,7 @@ static int match_extract_impl(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw
     T.N = g.N; T.C = pr.Cin; T.H1 = g.H1; T.W1 = g.W1; T.maxh = maxh; T.maxw = maxw;
     T.bs = g.bs; T.nwords = P.nwords; T.gb = P.gb; T.M = P.M; T.exact = exact ? 1 : 0;
     T.thr = prob_threshold;
+    T.mark = ctx->opt.debug_todo ? 1 : 0;
     T.todo = P.todo; T.todo_mask = P.todo_mask; T.ntodo = P.ntodo;
     T.vmin = P.vmin; T.vinv = P.vinv;
     T.index_thr = P.index_thr; T.score_thr = P.score_thr; T.n_untouched = P.n_untouched;

@@ -8,11 +8,20 @@
 // every slab value once for 64 partial sums: half the wavefronts per output, and the FP32 pipe
 // becomes the bound again.
 //
-// Work decomposition: CTA = NW consumer warps + 1 TMA producer warp = a tile of 2*NW output rows x
-// 128 columns; warp w owns rows y0+2w and y0+2w+1, lane l four consecutive pixels of both (their
-// C frame-1 values, pre-multiplied by -2, stay in registers: 2 x 4 x C).  Slab rows stream through
-// the same TMA + full/empty mbarrier ring as in match_kernels.cuh; at slab row j the warp computes
-// window row d0 = j - 2w for its first output row and d0 - 1 for the second.
+// Work decomposition: CTA = NW warps, ALL of them consumers = a tile of 2*NW output rows x 128
+// columns; warp w owns rows y0+2w and y0+2w+1, lane l four consecutive pixels of both (their C
+// frame-1 values, pre-multiplied by -2, stay in registers: 2 x 4 x C).  The kernel needs ~230
+// registers, i.e. two warps per scheduler: eight warps fill the four schedulers evenly, a ninth
+// (a dedicated TMA producer) would cap every warp at 168 registers.  So the ring is refilled by
+// the consumers themselves: the warp whose arrival completes a slot's `empty` phase (it sees the
+// phase complete right after its own arrive; a compare-and-swap on a per-slot counter makes it
+// exactly one) issues the TMA load of the row that takes the slot next.  At slab row j the warp
+// computes window row d0 = j - 2w for its first output row and d0 - 1 for the second.
+//
+// The per-row code of the common case (both output rows inside their windows) is straight-line:
+// the blocks of a window row are unrolled and the epilogue has no branch, so that the scheduler
+// can issue one block's epilogue (ALU / XU pipes) under the next block's FFMA2 stream -- with two
+// warps per scheduler there is nobody else to hide it.
 //
 // SSD form: v' = |b|^2 - 2 a.b  (the norm row rides in the ring as one more "channel" whose weight
 // is the constant 1).  |a|^2 is constant per pixel, so minima, their order and the soft-max
@@ -38,11 +47,25 @@ template <int NW, int PF>
 struct Sweep2Cfg {
   static constexpr int kWarps = NW;
   static constexpr int kCThreads = NW * 32;
-  static constexpr int kThreads = kCThreads + 32;
+  static constexpr int kThreads = kCThreads;  // no producer warp
   static constexpr int kTH = 2 * NW;
   static constexpr int kNSlot = 2 * NW + PF;
   static constexpr int kPx = 2 * kP;  // pixels per thread
 };
+
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 
 // packed block of both rows: acc2[row][pp][j] = sum_k a2[row][k][pp] * b[k][2pp + j] + nb[2pp + j]
 template <int CT, int JW>
@@ -104,6 +127,7 @@ struct Epi2 {
   int wb[NQ];
   float S[WTA ? 1 : NQ];
   int vfrom[WTA ? 1 : NQ];
+  unsigned rowbits[WTA ? 1 : NQ];  // shortlist bits of the window row in progress (bit = block of the row)
   float tau;
   unsigned *mask;  // [nwords][NQ][kCThreads] words, this thread's column
 
@@ -119,6 +143,7 @@ struct Epi2 {
       if (!WTA) {
         S[q] = 0.0f;
         vfrom[q] = 0;
+        rowbits[q] = 0u;
       }
     }
     if (!WTA)
@@ -127,15 +152,20 @@ struct Epi2 {
 
   // one output row of the thread (ROW compile-time), one skewed block: acc2[pp][r].x is pixel 2pp at
   // dx = 8*blk + r, .y pixel 2pp+1 at dx = 8*blk - 1 + r
-  template <int ROW, int R>
+  // MAYBE_FIRST: blk may be 0 (the dx = -1 slot of the odd pixels is masked)
+  template <int ROW, int R, bool MAYBE_FIRST>
   __device__ __forceinline__ void block(float2 (&acc2)[2][R], int dy, int blk) {
     const float inf = __int_as_float(0x7f800000);
     const int dx0 = blk * kR;
-    if (blk == 0) {  // dx = -1 of the odd pixels
+    if (P.dbg & 1) {  // tuning: no epilogue (results are wrong), keeps the sums alive
+      m[ROW * kP] = fminf(m[ROW * kP], acc2[0][0].x + acc2[1][R - 1].y);
+      return;
+    }
+    if (MAYBE_FIRST && blk == 0) {  // dx = -1 of the odd pixels
       acc2[0][0].y = inf;
       acc2[1][0].y = inf;
     }
-    if (dx0 + R > P.g.maxw) {  // past the window (last block only)
+    if ((R != kR || MAYBE_FIRST) && dx0 + R > P.g.maxw) {  // past the window (last block only)
 #pragma unroll
       for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
@@ -165,9 +195,7 @@ struct Epi2 {
       }
     }
     if (WTA) return;
-    const int bit = P.gb == 1 ? bid : bid / P.gb;
-    bool cand = false;
-    float emax[kP];
+    // (the host only picks this kernel when one shortlist bit is one block: gb == 1)
 #pragma unroll
     for (int pp = 0; pp < 2; ++pp) {
       const int q0 = ROW * kP + 2 * pp;
@@ -187,23 +215,36 @@ struct Epi2 {
       }
       S[q0] = fmaf(S[q0], sc0, eb2.x);
       S[q0 + 1] = fmaf(S[q0 + 1], sc1, eb2.y);
-      emax[2 * pp] = ex;
-      emax[2 * pp + 1] = ey;
       if (P.nwords) {
         // everything before a new minimum that rescaled the old one below the threshold is dead
-        vfrom[q0] = sc0 < P.p_clear ? bit : vfrom[q0];
-        vfrom[q0 + 1] = sc1 < P.p_clear ? bit : vfrom[q0 + 1];
+        vfrom[q0] = sc0 < P.p_clear ? bid : vfrom[q0];
+        vfrom[q0 + 1] = sc1 < P.p_clear ? bid : vfrom[q0 + 1];
         // p_k(final) <= e_k / S(now): an entry of this block can end above the threshold only if
-        // the block's largest term exceeds thr * S
-        cand |= ex > P.thr_lo * S[q0];
-        cand |= ey > P.thr_lo * S[q0 + 1];
+        // the block's largest term exceeds thr * S.  Collected per window row, flushed by row_end.
+        rowbits[q0] |= ex > P.thr_lo * S[q0] ? 1u << blk : 0u;
+        rowbits[q0 + 1] |= ey > P.thr_lo * S[q0 + 1] ? 1u << blk : 0u;
       }
     }
-    if (cand) {
+  }
+
+  // after the last block of window row dy of output row ROW: move the row's shortlist bits into
+  // the per-pixel bitmap in shared memory (the only data-dependent branch of the sweep)
+  template <int ROW>
+  __device__ __forceinline__ void row_end(int dy) {
+    if (WTA) return;
+    unsigned any = 0u;
+#pragma unroll
+    for (int p = 0; p < kP; ++p) any |= rowbits[ROW * kP + p];
+    if (any) {
+      const int bit0 = dy * P.g.bs.per_row();
+      const int w0 = bit0 >> 5, sh = bit0 & 31;
 #pragma unroll
       for (int p = 0; p < kP; ++p) {
         const int q = ROW * kP + p;
-        if (emax[p] > P.thr_lo * S[q]) mask[((bit >> 5) * NQ + q) * kCThreads] |= 1u << (bit & 31);
+        const unsigned long long v = (unsigned long long)rowbits[q] << sh;
+        if ((unsigned)v) mask[(w0 * NQ + q) * kCThreads] |= (unsigned)v;
+        if ((unsigned)(v >> 32)) mask[((w0 + 1) * NQ + q) * kCThreads] |= (unsigned)(v >> 32);
+        rowbits[q] = 0u;
       }
     }
   }
@@ -370,7 +411,29 @@ __device__ __forceinline__ void sweep2_tile_end(Epi2<Cfg, CT, EPI> &E, const flo
   if (P.n_untouched && untouched) atomicAdd(P.n_untouched + n, (unsigned long long)untouched);
 }
 
-template <class Cfg, int CT, int EPI>
+// Refill of ring slot `slot` with row `seq` of this CTA's row sequence (tile seq / rows_total, slab
+// row seq % rows_total), issued by one lane.
+__device__ __forceinline__ void sweep2_issue(const CUtensorMap *tmap, const CUtensorMap *tmap_nb, const SweepGeom &g,
+                                             float *ring, uint64_t *full, uint32_t seq, int slot, int rows_total, int th,
+                                             uint32_t slab_bytes) {
+  const int tl = (int)(seq / (uint32_t)rows_total), j = (int)(seq - (uint32_t)tl * rows_total);
+  const int tile = blockIdx.x + tl * gridDim.x;
+  const int tx = tile % g.tiles_x;
+  const int ty = (tile / g.tiles_x) % g.tiles_y;
+  const int n = tile / (g.tiles_x * g.tiles_y);
+  const int y = ty * th + j, xt = tx * kTW;
+  if (y < g.H2) {
+    mbar_arrive_expect_tx(&full[slot], slab_bytes);
+    tma_load_4d(ring + slot * g.slab_floats, tmap, &full[slot], xt, y, 0, n);
+    tma_load_4d(ring + slot * g.slab_floats + g.nb_off, tmap_nb, &full[slot], xt, y, 0, n);
+  } else {
+    mbar_arrive(&full[slot]);  // row below the frame: only masked pixels read it
+  }
+}
+
+// N8: number of full 8-wide blocks per window row when known at compile time (4 = a 33..34 wide
+// window with a 2-wide tail) so that the row body is straight-line code; 0 = generic (rolled).
+template <class Cfg, int CT, int EPI, int N8>
 __global__ void __launch_bounds__(Cfg::kThreads, 1)
 match_sweep2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_nb,
                     const ExtractParams P) {
@@ -383,7 +446,8 @@ match_sweep2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   float *ring = reinterpret_cast<float *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)g.nslot * g.slab_floats);
   uint64_t *empty = full + Cfg::kNSlot;
-  unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
+  unsigned *issued = reinterpret_cast<unsigned *>(empty + Cfg::kNSlot);  // refills issued per slot
+  unsigned *extra = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(full) + kBar2Bytes);
 
   constexpr int kWarps = Cfg::kWarps, kTH = Cfg::kTH;
   const int kNSlot = g.nslot;
@@ -391,8 +455,10 @@ match_sweep2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   const int rows_total = kTH + g.maxh - 1;
   const uint32_t slab_bytes = (uint32_t)((g.C + 1) * g.WB * sizeof(float));
   const int slab_floats = g.slab_floats;
-  const int n8 = g.bs.n8;
-  const bool wide_tail = g.bs.tail_r == kR;
+  const int n8 = N8 ? N8 : g.bs.n8;
+  const bool wide_tail = N8 ? false : g.bs.tail_r == kR;
+  const int my_tiles = (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t seq_total = (uint32_t)my_tiles * (uint32_t)rows_total;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap);
@@ -400,38 +466,14 @@ match_sweep2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     for (int s = 0; s < kNSlot; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kWarps);
+      issued[s] = 0u;
     }
     fence_mbar_init();
+    for (uint32_t s = 0; s < (uint32_t)kNSlot && s < seq_total; ++s)
+      sweep2_issue(&tmap, &tmap_nb, g, ring, full, s, (int)s, rows_total, kTH, slab_bytes);
   }
   __syncthreads();
 
-  if (warp == kWarps) {
-    // ---------------- producer warp (as in run_sweep)
-    if (lane == 0) {
-      uint32_t seq = 0;
-      for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
-        const int tx = tile % g.tiles_x;
-        const int ty = (tile / g.tiles_x) % g.tiles_y;
-        const int n = tile / (g.tiles_x * g.tiles_y);
-        const int y0 = ty * kTH, xt = tx * kTW;
-        for (int j = 0; j < rows_total; ++j, ++seq) {
-          const int slot = (int)(seq % kNSlot);
-          const uint32_t inst = seq / kNSlot;
-          if (inst > 0) mbar_wait_backoff(&empty[slot], (inst - 1) & 1u);
-          if (y0 + j < g.H2) {
-            mbar_arrive_expect_tx(&full[slot], slab_bytes);
-            tma_load_4d(ring + slot * slab_floats, &tmap, &full[slot], xt, y0 + j, 0, n);
-            tma_load_4d(ring + slot * slab_floats + g.nb_off, &tmap_nb, &full[slot], xt, y0 + j, 0, n);
-          } else {
-            mbar_arrive(&full[slot]);  // row below the frame: only masked pixels read it
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ---------------- consumer warps
   Epi2<Cfg, CT, EPI> epi(P, extra);
   uint32_t g0 = 0;
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
@@ -462,29 +504,74 @@ match_sweep2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     for (int j = 0; j < rows_total; ++j) {
       const uint32_t seq = g0 + (uint32_t)j;
       const int slot = (int)(seq % kNSlot);
-      mbar_wait(&full[slot], (seq / kNSlot) & 1u);
+      const uint32_t inst = seq / kNSlot;
+      if (!(P.dbg & 2)) mbar_wait(&full[slot], inst & 1u);   // dbg 2 (tuning): no ring protocol at all
       const int d0 = j - 2 * warp;  // window row of the first output row; the second is at d0 - 1
-      if (d0 >= 0 && d0 <= g.maxh) {
-        const float *brow = ring + slot * slab_floats + lane * kP;
+      const float *brow = ring + slot * slab_floats + lane * kP;
+      if (d0 >= 1 && d0 < g.maxh) {
+        // ---- both output rows inside their windows: straight-line when N8 is known
+        {
+          float2 acc2[2][2][kR];
+          dot2_block<CT, kR>(a2, brow, brow + g.nb_off, g.WB, acc2);
+          epi.template block<0, kR, true>(acc2[0], d0, 0);
+          epi.template block<1, kR, true>(acc2[1], d0 - 1, 0);
+        }
+        if (N8) {
+#pragma unroll
+          for (int blk = 1; blk < (N8 ? N8 : 1); ++blk) {
+            float2 acc2[2][2][kR];
+            dot2_block<CT, kR>(a2, brow + blk * kR, brow + g.nb_off + blk * kR, g.WB, acc2);
+            epi.template block<0, kR, false>(acc2[0], d0, blk);
+            epi.template block<1, kR, false>(acc2[1], d0 - 1, blk);
+          }
+        } else {
+          const int nwide = n8 + (wide_tail ? 1 : 0);
+#pragma unroll 1
+          for (int blk = 1; blk < nwide; ++blk) {
+            float2 acc2[2][2][kR];
+            dot2_block<CT, kR>(a2, brow + blk * kR, brow + g.nb_off + blk * kR, g.WB, acc2);
+            epi.template block<0, kR, false>(acc2[0], d0, blk);
+            epi.template block<1, kR, false>(acc2[1], d0 - 1, blk);
+          }
+        }
+        if (!wide_tail) {
+          float2 acc2[2][2][2];
+          dot2_block<CT, 2>(a2, brow + n8 * kR, brow + g.nb_off + n8 * kR, g.WB, acc2);
+          epi.template block<0, 2, false>(acc2[0], d0, n8);
+          epi.template block<1, 2, false>(acc2[1], d0 - 1, n8);
+        }
+        epi.template row_end<0>(d0);
+        epi.template row_end<1>(d0 - 1);
+      } else if (d0 == 0 || d0 == g.maxh) {
+        // ---- first / last slab row of this warp's window span: one output row only (rolled code)
         const int nwide = n8 + (wide_tail ? 1 : 0);
 #pragma unroll 1
         for (int blk = 0; blk < nwide; ++blk) {
           float2 acc2[2][2][kR];
           dot2_block<CT, kR>(a2, brow + blk * kR, brow + g.nb_off + blk * kR, g.WB, acc2);
-          if (d0 < g.maxh) epi.template block<0, kR>(acc2[0], d0, blk);
-          if (d0 >= 1) epi.template block<1, kR>(acc2[1], d0 - 1, blk);
+          if (d0 == 0) epi.template block<0, kR, true>(acc2[0], d0, blk);
+          else epi.template block<1, kR, true>(acc2[1], d0 - 1, blk);
         }
         if (!wide_tail) {
           float2 acc2[2][2][2];
           dot2_block<CT, 2>(a2, brow + n8 * kR, brow + g.nb_off + n8 * kR, g.WB, acc2);
-          if (d0 < g.maxh) epi.template block<0, 2>(acc2[0], d0, n8);
-          if (d0 >= 1) epi.template block<1, 2>(acc2[1], d0 - 1, n8);
+          if (d0 == 0) epi.template block<0, 2, false>(acc2[0], d0, n8);
+          else epi.template block<1, 2, false>(acc2[1], d0 - 1, n8);
         }
+        if (d0 == 0) epi.template row_end<0>(d0);
+        else epi.template row_end<1>(d0 - 1);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[slot]);  // this warp is done with the row
+      if (lane == 0 && !(P.dbg & 2)) {
+        // done with the row; whoever completes the slot's `empty` phase loads its next tenant
+        mbar_arrive(&empty[slot]);
+        const uint32_t next = seq + (uint32_t)kNSlot;
+        if (next < seq_total && mbar_test(&empty[slot], inst & 1u) && atomicCAS(&issued[slot], inst, inst + 1u) == inst)
+          sweep2_issue(&tmap, &tmap_nb, g, ring, full, next, slot, rows_total, kTH, slab_bytes);
+      }
     }
-    sweep2_tile_end<Cfg, CT, EPI>(epi, a2, n, yr, x0);
+    if (!(P.dbg & 4)) sweep2_tile_end<Cfg, CT, EPI>(epi, a2, n, yr, x0);   // dbg 4 (tuning): no resolve / stores
+    else if (epi.m[0] == 123.456f) P.resc[0] = 1;
     g0 += (uint32_t)rows_total;
   }
 }

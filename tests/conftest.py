@@ -54,3 +54,4 @@ def _reset_tuning_options(request):
             ctx.set_option("ssd_form", "auto")
             ctx.set_option("no_small_tiles", "0")
             ctx.set_option("sweep", "0")
+            ctx.set_option("conv", "0")

@@ -175,3 +175,30 @@ def test_two_row_sweep_variant_vs_oracle(dm, oracle, shape, data):
     finally:
         ctx.set_option("sweep", "0")
         ctx.set_option("ssd_form", "auto")
+
+
+@pytest.mark.parametrize("kind,layers,shape,pads", [
+    ("filter", [[3, 5, 5, 8], [4, 16, 16, 10]], (2, 3, 180, 320), (0, 0, 0, 0)),   # c1: full layer, tanh, connection table
+    ("filter", [[3, 5, 5, 10]], (1, 3, 90, 150), (2, 2, 2, 2)),                     # c3's prefilter with zero padding
+    ("radial", [[3, 1, 17, 5], [5, 17, 1, 10]], (2, 3, 100, 216), (0, 0, 0, 0)),    # c4's radial net: 1 x 17 then 17 x 1
+    ("radial", [[1, 7, 9, 4]], (1, 1, 40, 300), (0, 0, 0, 0)),                      # one input plane: the second K half is empty
+])
+def test_tensor_core_filter_layers_vs_default_kernel(dm, kind, layers, shape, pads):
+    """The opt-in tcgen05 convolution (filter_tc.cu, option conv = 2: kind::tf32 with a three-term hi / lo
+    split, accumulators in TMEM) against the default CUDA-core kernel -- itself held to 1e-4 of the
+    fp32 oracle by test_gpu_parity.py -- at the feature bar."""
+    rng = np.random.default_rng(5)
+    ctx = dm.default_context()
+    flt = dm.getFilter(dm.Geometry(layers=layers), rng) if kind == "filter" else dm.getRadialFilter(dict(layers=layers), rng)
+    x = rng.standard_normal(shape).astype(np.float32)
+    base = flt.forward(x, pads)
+    ctx.set_option("conv", "2")
+    try:
+        l0 = ctx.launch_count()
+        got = flt.forward(x, pads)
+        assert ctx.launch_count() - l0 == len(layers)
+    finally:
+        ctx.set_option("conv", "0")
+    scale = max(float(np.abs(base).max()), 1.0)
+    assert float(np.abs(got - base).max()) <= 1e-4 * scale, float(np.abs(got - base).max())
+    assert not np.array_equal(got, base)          # a different kernel really ran
