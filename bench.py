@@ -629,7 +629,7 @@ def bench_row_bands(dm, dm_parallel, dist, rank, world, ctx, pairs=12, warmup=3)
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        for k in ("index", "pmax"):
+        for k in ("index", "pmax"):   # for the breakdown: what one NCCL gather of the same bytes costs when nothing overlaps
             dm_parallel.gather_bands_inplace(m.full[0][k], m.hb, rank, dist)
         g1.record()
         torch.cuda.synchronize()
@@ -640,11 +640,12 @@ def bench_row_bands(dm, dm_parallel, dist, rank, world, ctx, pairs=12, warmup=3)
     ok = bool(((idx - 1) // mh == c + fy).all() and ((idx - 1) % mh == c + fx).all()) and tuple(idx.shape) == (h1, w1)
     per_pair = float(ms.item()) / pairs
     slots = 2.0 * Cb * mh * mh * h1 * w1
-    return {"config": "c5: 1920x1080, 65x65, C=10, %d row band(s) of %d rows + 64-row halo, in-place all_gather "
-                      "of index+pmax on a side stream" % (world, m.hb),
+    return {"config": "c5: 1920x1080, 65x65, C=10, %d row band(s) of %d rows + 64-row halo, band outputs (index, pmax) "
+                      "handed to the other ranks on a side stream" % (world, m.hb),
+            "gather": m.gather, "gather_fallback_reason": getattr(m, "gather_fallback_reason", None),
             "scaling": "strong", "n_gpus": world, "pairs": pairs, "ms_per_pair": per_pair,
             "pairs_per_s": 1e3 / per_pair, "band_sweep_ms": float(sweep_ms.item()),
-            "gather_ms_exposed_if_serial": float(gather_ms.item()),
+            "nccl_gather_ms_if_serial": float(gather_ms.item()),
             "gather_bytes_per_rank": int(m.hb * w1 * 12),
             "alu_frac_aggregate": slots / (per_pair * 1e-3) / (world * 148 * 128 * 1.965e9),
             "planted_flow_recovered": ok}

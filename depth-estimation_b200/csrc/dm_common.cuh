@@ -67,9 +67,10 @@ struct dm_ctx {
   int device = 0;
   dm::Options opt;
   // device counters of the most recent dm_match_extract on this context (dm_last_counts)
-  // Launch plans: what a call computes once per (kernel, shape) instead of once per call -- the
-  // dynamic shared-memory attribute already granted to a kernel, occupancy answers, encoded tensor
-  // maps (keyed by base pointer + geometry; a steady-state caller passes the same buffers).
+  // Launch plans: what a call computes once per (kernel, shape) instead of once per call.  Encoded
+  // tensor maps live here (keyed by base pointer + geometry; a steady-state caller passes the same
+  // buffers); the dynamic shared-memory grants and occupancy answers are per DEVICE (FuncPlan tables
+  // in dm_context.cu), because function attributes are.
   struct FuncPlan {
     const void *fn;
     int threads;
@@ -77,7 +78,6 @@ struct dm_ctx {
     int per_sm;       // occupancy at (threads, smem_occ); 0 = not asked yet
     size_t smem_occ;
   };
-  std::vector<FuncPlan> func_plans;
   struct MapPlan {
     const void *base;
     uint64_t dims[4], strides[3];

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <utility>
 
 #include "dm_common.cuh"
@@ -204,14 +205,22 @@ int tensor_map_4d(dm_ctx *ctx, CUtensorMap *map, const float *base, const uint64
   return DM_OK;
 }
 
+// Function attributes belong to the device, not to a dm_ctx: two contexts that shared a kernel but
+// kept separate books lowered each other's dynamic shared-memory grant.  One table per device,
+// process-wide; a grant is only ever raised.
+static std::mutex g_plan_mutex;
+static std::vector<dm_ctx::FuncPlan> g_func_plans[64];
+
 static dm_ctx::FuncPlan *func_plan(dm_ctx *ctx, const void *fn) {
-  for (auto &p : ctx->func_plans)
+  auto &plans = g_func_plans[ctx->device & 63];
+  for (auto &p : plans)
     if (p.fn == fn) return &p;
-  ctx->func_plans.push_back({fn, 0, 0, 0, 0});
-  return &ctx->func_plans.back();
+  plans.push_back({fn, 0, 0, 0, 0});
+  return &plans.back();
 }
 
 int ensure_func_smem(dm_ctx *ctx, const void *fn, size_t smem) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
   dm_ctx::FuncPlan *p = func_plan(ctx, fn);
   if (smem <= p->smem) return DM_OK;
   DM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -220,6 +229,7 @@ int ensure_func_smem(dm_ctx *ctx, const void *fn, size_t smem) {
 }
 
 int blocks_per_sm(dm_ctx *ctx, const void *fn, int threads, size_t smem) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
   dm_ctx::FuncPlan *p = func_plan(ctx, fn);
   if (p->per_sm > 0 && p->threads == threads && p->smem_occ == smem) return p->per_sm;
   int per_sm = 1;

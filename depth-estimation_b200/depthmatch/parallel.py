@@ -88,34 +88,75 @@ class RowBandMatcher:
     """BASELINE config 5: a stream of single large frame pairs, each cut in `world` equal row bands
     (SURVEY 8e).  Per pair a rank runs the fused kernel on its band -- frame-1 rows [y0, y1),
     frame-2 rows [y0, y1 + maxh - 1): the halo is re-read from the source, never exchanged -- with
-    the kernel writing straight into this rank's slice of the final maps, then the band outputs
-    are gathered in place on a side stream, so the gather of pair i overlaps the sweep of pair
-    i+1 (two result sets alternate).
+    the kernel writing straight into this rank's slice of the final maps; then the band is handed
+    to the other ranks on a side stream, under the next pair's sweep (two result sets alternate).
+
+    Two ways to hand the band over (`gather`):
+      "peer"  the final maps live in symmetric memory (torch.distributed._symmetric_memory: every
+              rank maps every other rank's buffer over NVLink / NVSwitch); a rank copies its band
+              slice into each peer's map with device-to-device copies, which the copy engines
+              execute -- the sweep is a persistent kernel that owns every SM's register file, an
+              SM-resident collective kernel can only run in the gaps between sweeps -- followed by
+              one symmetric-memory barrier.
+      "nccl"  one in-place all_gather_into_tensor per output (gather_bands_inplace).
+    "auto" tries "peer" and falls back to "nccl" (no P2P mapping, single rank, CPU tests).
 
         m = RowBandMatcher(dm, h1, w1, maxh, maxw, rank, world, dist, want=("index", "pmax"))
         h = m.step(in1, in2)      # torch CUDA tensors [C,H1,W1], [C,H2,W2], every rank holds them
         maps = h.wait()           # {"index": [h1, w1], ...} on every rank
     """
 
-    def __init__(self, dm, h1, w1, maxh, maxw, rank, world, dist=None, want=("index", "pmax"), ctx=None):
+    def __init__(self, dm, h1, w1, maxh, maxw, rank, world, dist=None, want=("index", "pmax"), ctx=None,
+                 gather="auto"):
         import torch
         self.dm, self.maxh, self.maxw, self.rank, self.world, self.dist = dm, maxh, maxw, rank, world, dist
         self.h1, self.w1, self.want = h1, w1, tuple(want)
         self.hb, self.bands = equal_row_bands(h1, world, maxh)
         dt = {"index": torch.int64, "index_thr": torch.int64}
-        self.full = [{k: torch.zeros((world * self.hb, w1), dtype=dt.get(k, torch.float32), device="cuda")
-                      for k in self.want} for _ in range(2)]
+        shape = (world * self.hb, w1)
+        self.gather, self.sym, self.peers = "none", None, None
+        if world > 1 and gather in ("auto", "peer"):
+            try:
+                self._setup_peer(torch, shape, dt)
+                self.gather = "peer"
+            except Exception as e:  # no symmetric memory on this box / build: NCCL does the gather
+                if gather == "peer":
+                    raise
+                self.gather_fallback_reason = "%s: %s" % (type(e).__name__, str(e)[:200])
+        if self.gather != "peer":
+            self.full = [{k: torch.zeros(shape, dtype=dt.get(k, torch.float32), device="cuda") for k in self.want}
+                         for _ in range(2)]
+            if world > 1:
+                self.gather = "nccl"
         self.ctx = ctx
         self.side = torch.cuda.Stream() if world > 1 else None
-        self.gathered = [None, None]   # event: the gather that last wrote result set i is complete
+        self.gathered = [None, None]   # event: the hand-over that last wrote result set i is complete
         self.i = 0
+
+    def _setup_peer(self, torch, shape, dt):
+        import torch.distributed as tdist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = tdist.group.WORLD
+        self.full, self.sym, self.peers = [], [], []
+        for _ in range(2):
+            maps, hdls, views = {}, {}, {}
+            for k in self.want:
+                t = symm_mem.empty(shape, dtype=dt.get(k, torch.float32), device=torch.device("cuda", torch.cuda.current_device()))
+                t.zero_()
+                hdl = symm_mem.rendezvous(t, group)
+                maps[k], hdls[k] = t, hdl
+                views[k] = [hdl.get_buffer(r, shape, t.dtype) if r != self.rank else t for r in range(self.world)]
+            self.full.append(maps)
+            self.sym.append(hdls)
+            self.peers.append(views)
+        torch.cuda.synchronize()
 
     class _Handle:
         def __init__(self, maps, event, h1):
             self.maps, self.event, self.h1 = maps, event, h1
 
         def wait(self):
-            """Orders the caller's current stream after the gather and returns the full maps."""
+            """Orders the caller's current stream after the hand-over and returns the full maps."""
             import torch
             if self.event is not None:
                 torch.cuda.current_stream().wait_event(self.event)
@@ -128,7 +169,7 @@ class RowBandMatcher:
         full = self.full[s]
         cur = torch.cuda.current_stream()
         if self.gathered[s] is not None:
-            cur.wait_event(self.gathered[s])   # the gather two steps ago still reads this set
+            cur.wait_event(self.gathered[s])   # the hand-over two steps ago still reads / writes this set
         y0, y1, hy1 = self.bands[self.rank]
         if y1 > y0:
             a, b = band_inputs(in1, in2, self.bands[self.rank])
@@ -140,8 +181,19 @@ class RowBandMatcher:
         done.record(cur)
         with torch.cuda.stream(self.side):
             self.side.wait_event(done)
-            for k in self.want:
-                gather_bands_inplace(full[k], self.hb, self.rank, self.dist)
+            if self.gather == "peer":
+                if y1 > y0:
+                    for k in self.want:
+                        src = full[k][y0:y1]
+                        for r in range(self.world):
+                            if r != self.rank:
+                                self.peers[s][k][r][y0:y1].copy_(src, non_blocking=True)
+                # every rank's copies are stream-ordered before its arrival at the barrier: past it,
+                # all bands have landed in this rank's maps
+                self.sym[s][self.want[0]].barrier(channel=s)
+            else:
+                for k in self.want:
+                    gather_bands_inplace(full[k], self.hb, self.rank, self.dist)
             ev = torch.cuda.Event()
             ev.record(self.side)
         self.gathered[s] = ev

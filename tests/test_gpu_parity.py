@@ -1128,3 +1128,23 @@ def test_windows_beyond_the_tiled_kernel_fall_back_to_the_untiled_one(dm, oracle
         np.testing.assert_array_equal(got["min_ssd"].reshape(-1), vol.min(-1))
         np.testing.assert_allclose(got["pmax"].reshape(-1), pmax, rtol=1e-4)
         np.testing.assert_array_equal(dm.match_volume(in1, in2, mh, mw, exact=True).reshape(-1, mh * mw), vol)
+
+
+def test_two_contexts_do_not_lower_each_others_shared_memory_grant(dm):
+    """Function attributes belong to the device: a second context that launches the same kernel with
+    a smaller dynamic shared-memory size must not shrink the grant the first one relies on (round 2:
+    a per-context cache did exactly that -> cudaLaunchKernel 'invalid argument' on the next call)."""
+    import torch
+    c1, c2 = dm.Context(0), dm.Context(0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    big2 = torch.randn((3, 10, 120, 400), device="cuda", generator=g)
+    big1 = big2[:, :, 16:16 + 88, 16:16 + 368].contiguous()
+    sm2 = torch.randn((3, 10, 200, 400), device="cuda", generator=g)
+    sm1 = sm2[:, :, 4:4 + 192, 4:4 + 392].contiguous()
+    want = ("index", "pmax", "score_thr")
+    a = dm.match_extract(big1, big2, 33, 33, want=want, ctx=c1)          # large ring
+    dm.match_extract(sm1, sm2, 9, 9, want=want, ctx=c2)                  # same kernel, small ring
+    b = dm.match_extract(big1, big2, 33, 33, want=want, ctx=c1)          # must still launch
+    torch.cuda.synchronize()
+    for k in want:
+        assert torch.equal(a[k], b[k]), k
