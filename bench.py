@@ -44,7 +44,7 @@ BYTES_VOLUME = BYTES_FUSED + 4 * H1 * W1 * K
 ALU_SLOTS = 2 * C * K * H1 * W1
 # dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel per launch / pairs per launch, from
 # this round's `ncu --set full` capture (file named next to it; None until a capture of this build exists)
-NCU_TRAFFIC = {"bytes_per_pair": (75.497216e6 + 3.643392e6) / 4, "source": "profiles/r01_ncu_fused_kernel.md"}
+NCU_TRAFFIC = {"bytes_per_pair": (73.1e6 + 5.1e6) / 4, "source": "profiles/r02_ncu_kernels.md, launch #2 (4 pairs)"}
 METRIC = "frame-pairs/sec @640x360, 33x33 window"
 WORKLOAD = "north: 640x360 feature maps, C=10, 33x33 window, fused match+extract"
 

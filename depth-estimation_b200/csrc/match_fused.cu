@@ -281,21 +281,24 @@ struct ExtractEpi {
   __device__ __forceinline__ void tile_rescore(const float2 (&a2)[CT][2], int n, int y, int x0) {
     if (!DOT || y >= P.g.H1) return;
     if (WTA && !P.min_ssd) return;
+    if (!P.in2) return;   // statistics pass of the soft-max volume: min and sum stay in the dot form (minus |a|^2),
+                          // which is what the volume sweep that follows computes too
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
       if (x0 + p >= P.g.W1) continue;
       const int dy = (idx[p] - 1) / P.g.maxw, dx = (idx[p] - 1) % P.g.maxw;
       const float *b = P.in2 + (long long)n * P.s2n + (long long)(y + dy) * P.s2y + (x0 + p + dx);
-      float acc = 0.0f;
+      float acc = 0.0f, na = 0.0f;
 #pragma unroll
       for (int k = 0; k < CT; ++k) {
         const float2 av = a2[k][p >> 1];
         const float a = -0.5f * ((p & 1) ? av.y : av.x);
+        na = fmaf(a, a, na);
         const float d = a - (k < P.g.Cin ? __ldg(b + (long long)k * P.s2c) : 0.0f);
         acc = fmaf(d, d, acc);
       }
       if (!WTA) {
-        const float c = expf(acc - m[p]);
+        const float c = expf(acc - (m[p] + na));   // m is the dot-form minimum without |a|^2
         S[p] = fmaf(S[p] - 1.0f, c, 1.0f);
         e2[p] *= c;
         if (SOFT) {
@@ -551,6 +554,10 @@ struct VolumeParams {
   const float *vinv;   // [N][H1][W1] 1 / sum_k exp(min - v_k)
   float *out;          // [N][H1][W1][K]
   int debug;           // DM_VOLUME_DEBUG: 1 = skip the global stores, 2 = stores wrap into 32 MB
+  // soft-max volume in the dot form (probabilities only need 1e-4): twin launch on the norm bound
+  // as in the fused kernel; NULL = run unconditionally
+  const unsigned *stats;
+  float dot_limit;
 };
 
 // Store staging of the volume kernel.  The output tensor [px][K] gives every pixel a
@@ -689,18 +696,25 @@ struct VolumeEpi {
     }
   }
 
+  template <int CT>
+  __device__ __forceinline__ void tile_rescore(const float2 (&)[CT][2], int, int, int) {}
   __device__ __forceinline__ void tile_end(int, int, int) {}
 };
 
-template <int CT, bool EXACT>
+template <int CT, int MODE>
 __global__ void __launch_bounds__(VolumeCfg::kThreads, 1)
-match_volume_kernel(const __grid_constant__ CUtensorMap tmap, const VolumeParams P) {
+match_volume_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_nb,
+                    const VolumeParams P) {
+  if (P.stats) {  // twin launch: the norm bound picks the dot or the difference form
+    const bool dot_ok = __uint_as_float(P.stats[0]) + __uint_as_float(P.stats[1]) <= P.dot_limit;
+    if (dot_ok != (MODE == kDot)) return;
+  }
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ring = reinterpret_cast<float *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)P.g.nslot * P.g.slab_floats);
   float *stg = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full) + kBarBytes);
   VolumeEpi epi(P, stg);
-  run_sweep<VolumeCfg, CT, EXACT ? kExact : kFma>(&tmap, &tmap, P.g, ring, full, epi);
+  run_sweep<VolumeCfg, CT, MODE>(&tmap, &tmap_nb, P.g, ring, full, epi);
 }
 
 // ---------------------------------------------------------------- host side
@@ -1284,7 +1298,9 @@ extern "C" int dm_match_extract(dm_ctx *ctx, const dm_pair *in, int maxh, int ma
 namespace dm {
 
 // statistics pass for the soft-max volume: per-pixel min and 1/sum, nothing else
-static int launch_stats(Call &call, const Prepared &pr, bool exact, bool small, float *vmin, float *vinv) {
+static int launch_stats(Call &call, const Prepared &pr, int ssd_mode, bool small, float *vmin, float *vinv,
+                        const CUtensorMap *nbmap = nullptr, const unsigned *stats = nullptr, float dot_limit = 0.0f,
+                        const float *in2 = nullptr) {
   dm_ctx *ctx = call.ctx;
   const SweepGeom &g = pr.g;
   const int cfg_th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
@@ -1302,13 +1318,20 @@ static int launch_stats(Call &call, const Prepared &pr, bool exact, bool small, 
   set_middle(&P, g.maxw);
   P.min_ssd = vmin;
   P.pmax = vinv;
+  P.stats = stats;
+  P.dot_limit = dot_limit;
+  if (ssd_mode == kDot) {   // statistics in the dot form: no rescore list, the volume pass uses the same sums
+    P.g.nb_off = (P.g.C * P.g.WB + 31) & ~31;
+    P.g.slab_floats = P.g.nb_off + ((P.g.WB + 31) & ~31);
+    (void)in2;            // P.in2 stays NULL: no re-score of the winner, see ExtractEpi::tile_rescore
+  }
   const size_t extra = kBarBytes + (size_t)cfg_cthreads * kP * sizeof(unsigned);
   DM_CHECK(fit_ring(ctx, &P.g, cfg_th, cfg_nslot, extra));
   const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
-  const void *kfn = pick_extract(small, pr.CT, exact ? kExact : kFma, kEpiScores);
+  const void *kfn = pick_extract(small, pr.CT, ssd_mode, kEpiScores);
   DM_CHECK(ensure_func_smem(ctx, kfn, smem));
   const int grid = grid_for(ctx, kfn, cfg_threads, smem, g.ntiles);
-  void *args[] = {(void *)&pr.tmap, (void *)&pr.tmap, (void *)&P};
+  void *args[] = {(void *)&pr.tmap, (void *)(nbmap ? nbmap : &pr.tmap), (void *)&P};
   DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(cfg_threads), args, smem, ctx->stream));
   count_launch(ctx);
   return DM_OK;
@@ -1342,34 +1365,91 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
   P.vmin = P.vinv = nullptr;
   P.out = static_cast<float *>(p);
   P.debug = ctx->opt.volume_debug;
+  P.stats = nullptr;
+  P.dot_limit = 0.0f;
+  // soft-max volume of a large call: both sweeps in the dot form (half the FP32 work; the outputs
+  // are probabilities, whose 1e-4 bar the form meets under the same norm bound as the fused
+  // kernel -- no index is produced here, so there is nothing to rescore)
+  const bool big = (double)g.H1 * g.W1 * g.N * maxh * maxw * pr.Cin >= 5.0e8;
+  bool dot = mode == DM_VOLUME_NEG_SOFTMAX && !exact && big && ctx->opt.ssd_form != 1;
+  CUtensorMap nbmap = pr.tmap;
+  const unsigned *stats = nullptr;
+  float dot_limit = 0.0f;
+  SweepGeom gdot = g;
+  if (dot) {
+    gdot.nb_off = (g.C * g.WB + 31) & ~31;
+    gdot.slab_floats = gdot.nb_off + ((g.WB + 31) & ~31);
+    const size_t extra_v = kBarBytes + (size_t)VolumeCfg::kWarps * 2 * kStgPlane * sizeof(float);
+    dot = fit_ring(ctx, &gdot, VolumeCfg::kTH, VolumeCfg::kNSlot, extra_v) == DM_OK;
+  }
+  if (dot) {
+    const long long w2p = (g.W2 + 3) & ~3LL;
+    void *nbuf = nullptr, *st = nullptr;
+    DM_CHECK(call.alloc(&nbuf, (size_t)g.N * g.H2 * w2p * sizeof(float)));
+    DM_CHECK(call.alloc(&st, 256));
+    DM_CUDA(cudaMemsetAsync(st, 0, 2 * sizeof(unsigned), ctx->stream));
+    const int nthr = 256, nblk = ctx->num_sms * 8;
+    norm_kernel<<<nblk, nthr, 0, ctx->stream>>>(g.in1, g.s1n, g.s1c, g.s1y, g.N, pr.Cin, g.H1, g.W1, nullptr, 0, 0,
+                                                static_cast<unsigned *>(st));
+    norm_kernel<<<nblk, nthr, 0, ctx->stream>>>(pr.in2_dev, pr.s2n, pr.s2c, pr.s2y, g.N, pr.Cin, g.H2, g.W2,
+                                                static_cast<float *>(nbuf), (long long)g.H2 * w2p, w2p,
+                                                static_cast<unsigned *>(st) + 1);
+    count_launch(ctx, 2);
+    const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, 1u, (uint64_t)g.N};
+    const uint64_t strides[3] = {(uint64_t)w2p * 4, (uint64_t)g.H2 * w2p * 4, (uint64_t)g.H2 * w2p * 4};
+    const uint32_t box[4] = {(uint32_t)g.WB, 1u, 1u, 1u};
+    DM_CHECK(tensor_map_4d(ctx, &nbmap, static_cast<const float *>(nbuf), dims, strides, box));
+    stats = static_cast<const unsigned *>(st);
+    dot_limit = ctx->opt.ssd_form == 2 ? 3.0e38f : 1.0e-4f / ((float)(pr.Cin + 2) * 5.9604645e-8f);
+  }
   if (mode == DM_VOLUME_NEG_SOFTMAX) {
     void *s = nullptr;
     DM_CHECK(call.alloc(&s, npx * 2 * sizeof(float)));
     float *vmin = static_cast<float *>(s), *vinv = vmin + npx;
     Prepared ps = pr;  // the statistics sweep runs with the extraction kernel's tile height
     const long long big_tiles = (long long)g.tiles_x * ((g.H1 + ExtractCfg::kTH - 1) / ExtractCfg::kTH) * g.N;
-    const bool small = 2 * big_tiles < ctx->num_sms && !ctx->opt.no_small_tiles;  // e.g. the coarse scales
+    const bool small = 2 * big_tiles < ctx->num_sms && !ctx->opt.no_small_tiles && !dot;  // e.g. the coarse scales
     const int th = small ? ExtractCfgSmall::kTH : ExtractCfg::kTH;
     ps.g.tiles_y = (g.H1 + th - 1) / th;
     ps.g.ntiles = ps.g.tiles_x * ps.g.tiles_y * g.N;
-    DM_CHECK(launch_stats(call, ps, exact, small, vmin, vinv));
+    if (dot) {
+      // twin launch: the norm bound, read on the device, lets exactly one of the two run
+      DM_CHECK(launch_stats(call, ps, kDot, small, vmin, vinv, &nbmap, stats, dot_limit, pr.in2_dev));
+      DM_CHECK(launch_stats(call, ps, kFma, small, vmin, vinv, nullptr, stats, dot_limit));
+    } else {
+      DM_CHECK(launch_stats(call, ps, exact ? kExact : kFma, small, vmin, vinv));
+    }
     P.vmin = vmin;
     P.vinv = vinv;
   }
   const size_t extra = kBarBytes + (size_t)VolumeCfg::kWarps * 2 * kStgPlane * sizeof(float);
   DM_CHECK(fit_ring(ctx, &P.g, VolumeCfg::kTH, VolumeCfg::kNSlot, extra));
-  const size_t smem = ring_bytes(P.g, P.g.nslot) + extra;
-#define DM_PICKV(ct)                                                                  \
-  (exact ? (const void *)match_volume_kernel<ct, true> : (const void *)match_volume_kernel<ct, false>)
-  const void *kfn = pr.CT == 4 ? DM_PICKV(4) : (pr.CT == 10 ? DM_PICKV(10) : DM_PICKV(16));
+  auto launch_vol = [&](const VolumeParams &Q, const CUtensorMap &nb, int ssd_mode) -> int {
+    const size_t smem = ring_bytes(Q.g, Q.g.nslot) + extra;
+#define DM_PICKV(ct)                                                                                      \
+  (ssd_mode == kExact ? (const void *)match_volume_kernel<ct, kExact>                                     \
+                      : (ssd_mode == kDot ? (const void *)match_volume_kernel<ct, kDot> : (const void *)match_volume_kernel<ct, kFma>))
+    const void *kfn = pr.CT == 4 ? DM_PICKV(4) : (pr.CT == 10 ? DM_PICKV(10) : DM_PICKV(16));
 #undef DM_PICKV
-  DM_CHECK(ensure_func_smem(ctx, kfn, smem));
-  const int grid = grid_for(ctx, kfn, VolumeCfg::kThreads, smem, g.ntiles);
-  void *args[] = {(void *)&pr.tmap, (void *)&P};
+    DM_CHECK(ensure_func_smem(ctx, kfn, smem));
+    const int grid = grid_for(ctx, kfn, VolumeCfg::kThreads, smem, Q.g.ntiles);
+    void *args[] = {(void *)&pr.tmap, (void *)&nb, (void *)&Q};
+    DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(VolumeCfg::kThreads), args, smem, ctx->stream));
+    count_launch(ctx);
+    return DM_OK;
+  };
   prof_begin(ctx);
-  DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(VolumeCfg::kThreads), args, smem, ctx->stream));
+  if (dot) {
+    VolumeParams Pd = P;
+    Pd.g = gdot;
+    Pd.stats = P.stats = stats;
+    Pd.dot_limit = P.dot_limit = dot_limit;
+    DM_CHECK(launch_vol(Pd, nbmap, kDot));
+    DM_CHECK(launch_vol(P, pr.tmap, kFma));
+  } else {
+    DM_CHECK(launch_vol(P, pr.tmap, exact ? kExact : kFma));
+  }
   prof_end(ctx);
-  count_launch(ctx);
   return DM_OK;
 }
 }  // namespace dm

@@ -89,16 +89,18 @@ struct SweepGeom {
 //          largest norms keep that below the parity bar (see match_extract_impl).
 enum SsdMode { kFma = 0, kExact = 1, kDot = 2 };
 
-// kDot block: acc2[pp][j] = (na_even, na_odd) + nb[col] + sum_k (-2 a[k]) * b[k][col]; `a2`
-// holds -2a.  Same operation sequence for every (pixel, displacement): identical inputs give
-// bit-identical sums, so the ties of flat image regions stay ties.
+// kDot block: acc2[pp][j] = nb[col] + sum_k (-2 a[k]) * b[k][col] = v - |a|^2; `a2` holds -2a.  |a|^2
+// is constant per pixel: minima, their order and the soft-max differences are those of this sum
+// itself, so it never enters the loop (the epilogue adds it back where an SSD is reported).  The
+// first FFMA2 takes the norm as a broadcast addend, so a block is C packed operations per two
+// window entries, nothing else.  Same operation sequence for every (pixel, displacement):
+// identical inputs give bit-identical sums, so the ties of flat image regions stay ties.
 template <int CT, int JW>
-__device__ __forceinline__ void dot_block2(const float2 (&a2)[CT][2], const float2 (&na2)[2],
-                                           const float *bsrc, const float *nbsrc, int WB,
+__device__ __forceinline__ void dot_block2(const float2 (&a2)[CT][2], const float *bsrc, const float *nbsrc, int WB,
                                            float2 (&acc2)[2][JW]) {
   constexpr int NBF = JW == kR ? kNB : kP;
+  float nb[NBF];
   {
-    float nb[NBF];
     const float4 *src = reinterpret_cast<const float4 *>(nbsrc);
 #pragma unroll
     for (int j = 0; j < NBF / 4; ++j) {
@@ -108,11 +110,6 @@ __device__ __forceinline__ void dot_block2(const float2 (&a2)[CT][2], const floa
       nb[4 * j + 2] = t.z;
       nb[4 * j + 3] = t.w;
     }
-#pragma unroll
-    for (int pp = 0; pp < 2; ++pp)
-#pragma unroll
-      for (int j = 0; j < JW; ++j)
-        acc2[pp][j] = __fadd2_rn(na2[pp], make_float2(nb[2 * pp + j], nb[2 * pp + j]));
   }
 #pragma unroll
   for (int k = 0; k < CT; ++k) {
@@ -129,8 +126,10 @@ __device__ __forceinline__ void dot_block2(const float2 (&a2)[CT][2], const floa
 #pragma unroll
     for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-      for (int j = 0; j < JW; ++j)
-        acc2[pp][j] = __ffma2_rn(a2[k][pp], make_float2(b[2 * pp + j], b[2 * pp + j]), acc2[pp][j]);
+      for (int j = 0; j < JW; ++j) {
+        const float2 addend = k == 0 ? make_float2(nb[2 * pp + j], nb[2 * pp + j]) : acc2[pp][j];
+        acc2[pp][j] = __ffma2_rn(a2[k][pp], make_float2(b[2 * pp + j], b[2 * pp + j]), addend);
+      }
   }
 }
 
@@ -273,21 +272,12 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const CUtenso
         a2[k][1] = make_float2(a[2], a[3]);
       }
     }
-    float2 na2[2];
-    if (MODE == kDot) {
-      // |a|^2 with the same FMA chain the norm pre-pass uses for |b|^2, then a <- -2a (exact)
-      float na[kP] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (MODE == kDot) {   // a <- -2a (exact)
 #pragma unroll
       for (int k = 0; k < CT; ++k) {
-        na[0] = fmaf(a2[k][0].x, a2[k][0].x, na[0]);
-        na[1] = fmaf(a2[k][0].y, a2[k][0].y, na[1]);
-        na[2] = fmaf(a2[k][1].x, a2[k][1].x, na[2]);
-        na[3] = fmaf(a2[k][1].y, a2[k][1].y, na[3]);
         a2[k][0] = make_float2(-2.0f * a2[k][0].x, -2.0f * a2[k][0].y);
         a2[k][1] = make_float2(-2.0f * a2[k][1].x, -2.0f * a2[k][1].y);
       }
-      na2[0] = make_float2(na[0], na[1]);
-      na2[1] = make_float2(na[2], na[3]);
     }
     epi.tile_begin(n, y, x0);
 
@@ -304,7 +294,7 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const CUtenso
         for (int blk = 0; blk < nwide; ++blk) {
           float2 acc2[2][kR];
           if constexpr (MODE == kDot)
-            dot_block2<CT, kR>(a2, na2, brow + blk * kR, brow + g.nb_off + blk * kR, g.WB, acc2);
+            dot_block2<CT, kR>(a2, brow + blk * kR, brow + g.nb_off + blk * kR, g.WB, acc2);
           else
             ssd_block2<CT, EXACT, kR>(a2, brow + blk * kR, g.WB, acc2);
           float acc[kP][kR];
@@ -314,7 +304,7 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const CUtenso
         if (!wide_tail) {
           float2 acc2[2][2];
           if constexpr (MODE == kDot)
-            dot_block2<CT, 2>(a2, na2, brow + n8 * kR, brow + g.nb_off + n8 * kR, g.WB, acc2);
+            dot_block2<CT, 2>(a2, brow + n8 * kR, brow + g.nb_off + n8 * kR, g.WB, acc2);
           else
             ssd_block2<CT, EXACT, 2>(a2, brow + n8 * kR, g.WB, acc2);
           float acc[kP][2];

@@ -202,3 +202,20 @@ def test_tensor_core_filter_layers_vs_default_kernel(dm, kind, layers, shape, pa
     scale = max(float(np.abs(base).max()), 1.0)
     assert float(np.abs(got - base).max()) <= 1e-4 * scale, float(np.abs(got - base).max())
     assert not np.array_equal(got, base)          # a different kernel really ran
+
+
+@pytest.mark.parametrize("data", ["0.3", "unrelated"])
+def test_softmax_volume_of_a_large_call_vs_oracle(dm, oracle, data):
+    """dm_match_volume(NEG_SOFTMAX) on a call large enough for the dot form (both of its sweeps: the
+    statistics and the volume): every probability within 1e-4 of Minus + SoftMax on the CPU."""
+    maxh = maxw = 33
+    in1, in2 = _pair(10, 200, 400, maxh, maxw, data, 61)
+    ctx = dm.default_context()
+    l0 = ctx.launch_count()
+    got = dm.match_volume(in1, in2, maxh, maxw, softmax=True)
+    assert ctx.launch_count() - l0 == 6            # 2 norm passes + twin statistics + twin volume sweeps
+    want = oracle.neg_softmax(oracle.spatial_matching(in1, in2, maxh, maxw))
+    np.testing.assert_allclose(got, want.reshape(got.shape), rtol=1e-4, atol=1e-12)
+    dif = dm.match_volume(in1 * 4, in2 * 4, maxh, maxw, softmax=True)      # norms beyond the bound: difference form
+    want = oracle.neg_softmax(oracle.spatial_matching(in1 * 4, in2 * 4, maxh, maxw))
+    np.testing.assert_allclose(dif, want.reshape(dif.shape), rtol=1e-4, atol=1e-12)
