@@ -9,9 +9,9 @@ namespace dm {
 struct TcPlan {
   int ok;              // the layer fits the tensor-core kernel
   int KP, Ktot;        // kernel rows padded to 8 per input plane; n_in * KP
+  int KtotB;           // K extent of the weight operand: n_in * (KP + 4), one spare chunk per plane
   int G, ngroups;      // output planes per group (per GEMM), number of groups
   int Npad;            // G * kW padded to a multiple of 16
-  int RS;              // image-row ring slots (power of two >= kH)
   size_t smem;
 };
 

@@ -44,6 +44,8 @@ def run(name, flt, x, iters=20):
 
 def main():
     rng = np.random.default_rng(0)
+    if "--conv" in sys.argv:  # 2 = the tcgen05 kernel for the layers it can plan (filter_tc.cu)
+        dm.default_context().set_option("conv", int(sys.argv[sys.argv.index("--conv") + 1]))
     g = dm.Geometry(layers=[[3, 5, 5, 8], [4, 16, 16, 10]])
     x = torch.rand((2, 3, 360, 640), device="cuda")
     if "--one" in sys.argv:  # a short run for ncu
