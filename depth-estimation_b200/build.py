@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libdepthmatch.so")
 SOURCES = ["dm_context.cu", "match_fused.cu", "match_generic.cu", "extract.cu", "multiscale.cu",
            "radial.cu", "postprocess.cu", "filter.cu", "filter_tc.cu"]
-HEADERS = ["dm_common.cuh", "match_kernels.cuh", "match_sweep2.cuh", "filter_tc.cuh", os.path.join("..", "..", "include", "depthmatch.h")]
+HEADERS = ["dm_common.cuh", "match_kernels.cuh", "match_sweep2.cuh", "match_volume_px.cuh", "filter_tc.cuh", os.path.join("..", "..", "include", "depthmatch.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",

@@ -262,6 +262,7 @@ static int apply_option(Options *o, const char *name, const char *value) {
   else if (!strcmp(name, "volume_debug")) o->volume_debug = iv;
   else if (!strcmp(name, "sweep")) o->sweep = iv;
   else if (!strcmp(name, "conv")) o->conv = iv;
+  else if (!strcmp(name, "volume_kernel")) o->volume_kernel = iv;
   else if (!strcmp(name, "conv_tile")) {
     o->conv_tile = o->conv_target = 0;
     if (value) sscanf(value, "%d,%d", &o->conv_tile, &o->conv_target);
@@ -274,7 +275,7 @@ static void options_from_env(Options *o) {
       {"DM_SSD_FORM", "ssd_form"},       {"DM_NO_SMALL_TILES", "no_small_tiles"}, {"DM_NO_PIPELINE", "no_pipeline"},
       {"DM_DEBUG_TODO", "debug_todo"},   {"DM_PIPE_CHUNK", "pipe_chunk"},         {"DM_VOLUME_DEBUG", "volume_debug"},
       {"DM_CONV_TILE", "conv_tile"},     {"DM_SWEEP", "sweep"},
-      {"DM_CONV", "conv"}};
+      {"DM_CONV", "conv"},               {"DM_VOLUME_KERNEL", "volume_kernel"}};
   for (const auto &e : kEnv)
     if (const char *v = getenv(e[0])) {
       // flags set to the empty string or anything non-numeric count as "on"

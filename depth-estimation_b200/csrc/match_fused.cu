@@ -717,6 +717,10 @@ match_volume_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   run_sweep<VolumeCfg, CT, MODE>(&tmap, &tmap_nb, P.g, ring, full, epi);
 }
 
+}  // namespace dm
+#include "match_volume_px.cuh"
+namespace dm {
+
 // ---------------------------------------------------------------- host side
 static size_t ring_bytes(const SweepGeom &g, int nslot) {
   return (size_t)nslot * g.slab_floats * sizeof(float);
@@ -1376,6 +1380,7 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
   const unsigned *stats = nullptr;
   float dot_limit = 0.0f;
   SweepGeom gdot = g;
+  const float *nbuf_dev = nullptr;
   if (dot) {
     gdot.nb_off = (g.C * g.WB + 31) & ~31;
     gdot.slab_floats = gdot.nb_off + ((g.WB + 31) & ~31);
@@ -1399,6 +1404,7 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     const uint64_t strides[3] = {(uint64_t)w2p * 4, (uint64_t)g.H2 * w2p * 4, (uint64_t)g.H2 * w2p * 4};
     const uint32_t box[4] = {(uint32_t)g.WB, 1u, 1u, 1u};
     DM_CHECK(tensor_map_4d(ctx, &nbmap, static_cast<const float *>(nbuf), dims, strides, box));
+    nbuf_dev = static_cast<const float *>(nbuf);
     stats = static_cast<const unsigned *>(st);
     dot_limit = ctx->opt.ssd_form == 2 ? 3.0e38f : 1.0e-4f / ((float)(pr.Cin + 2) * 5.9604645e-8f);
   }
@@ -1438,14 +1444,88 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     count_launch(ctx);
     return DM_OK;
   };
+  // The strip kernel (match_volume_px.cuh) writes whole pixel streams with bulk copies; it needs
+  // 16-byte aligned runs of 4 pixels (W1 % 4 == 0) and two staging buffers of 16 streams next to a
+  // ring of maxh + 3 rows.  What it cannot take stays with the tiled kernel above.
+  PxGeom X = {};
+  CUtensorMap pxmap = pr.tmap, pxnb = pr.tmap;
+  bool strip = ctx->opt.volume_kernel != 1 && g.W1 % 4 == 0 && (reinterpret_cast<uintptr_t>(P.out) % 16) == 0;
+  size_t px_smem = 0;
+  if (strip) {
+    const BlockSchedule bs = g.bs;
+    const bool wide = bs.tail_r == kR;
+    X.WBs = kPxW - kP + bs.n8 * kR + (wide ? kNB : kP);
+    X.nb_off = (pr.CT * X.WBs + 31) & ~31;
+    X.pitch = dot ? X.nb_off + ((X.WBs + 31) & ~31) : X.nb_off;
+    X.nslot = maxh + kPxAhead;
+    X.nwide = bs.n8 + (wide ? 1 : 0);
+    const int rem = X.nwide % 4;
+    X.nbp = 2 * (X.nwide / 4) + (rem + 1) / 2;
+    X.ndg = (maxh + 3) / 4;
+    X.nfull = X.ndg * X.nbp;
+    X.items = X.nfull + (wide ? 0 : (maxh + 7) / 8);
+    X.strips = (g.W1 + kPxW - 1) / kPxW;
+    px_smem = ((size_t)X.nslot * X.pitch + 2 * (size_t)kPxW * K + 4 + (size_t)kPxARing * (pr.CT * kPxW + 2 * kPxW)) * sizeof(float) +
+              (2 * kPxMaxSlot + 4 + kPxARing) * sizeof(uint64_t);
+    strip = X.WBs <= 256 && X.nslot <= kPxMaxSlot && X.nwide >= 1 && px_smem <= ctx->smem_optin;
+  }
+  if (strip) {
+    // rows per unit: the split of the strips into row bands that fills the CTAs' waves best (a unit
+    // pays about three steps for its first maxh - 1 rows)
+    const long long per_band = (long long)g.N * X.strips;
+    long long best = -1;
+    for (int nb = 1; nb <= g.H1 && nb <= 64; ++nb) {
+      const int band = (g.H1 + nb - 1) / nb;
+      if (band < 8 && nb > 1) break;
+      const long long waves = (per_band * nb + ctx->num_sms - 1) / ctx->num_sms;
+      const long long cost = waves * (band + 3);
+      if (best < 0 || cost < best) {
+        best = cost;
+        X.band = band;
+      }
+    }
+    X.nbands = (g.H1 + X.band - 1) / X.band;
+    X.units = (int)(per_band * X.nbands);
+    const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, (uint64_t)pr.Cin, (uint64_t)g.N};
+    const uint64_t strides[3] = {(uint64_t)pr.s2y * 4, (uint64_t)pr.s2c * 4, (uint64_t)pr.s2n * 4};
+    const uint32_t box[4] = {(uint32_t)X.WBs, 1u, (uint32_t)pr.CT, 1u};
+    DM_CHECK(tensor_map_4d(ctx, &pxmap, pr.in2_dev, dims, strides, box));
+    if (dot) {
+      const long long w2p = (g.W2 + 3) & ~3LL;
+      const uint64_t ndims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, 1u, (uint64_t)g.N};
+      const uint64_t nstr[3] = {(uint64_t)w2p * 4, (uint64_t)g.H2 * w2p * 4, (uint64_t)g.H2 * w2p * 4};
+      const uint32_t nbox[4] = {(uint32_t)X.WBs, 1u, 1u, 1u};
+      DM_CHECK(tensor_map_4d(ctx, &pxnb, nbuf_dev, ndims, nstr, nbox));
+    }
+  }
+  auto launch_px = [&](const VolumeParams &Q, int ssd_mode) -> int {
+#define DM_PICKX(ct)                                                                                      \
+  (ssd_mode == kExact ? (const void *)match_volume_px_kernel<ct, kExact>                                  \
+                      : (ssd_mode == kDot ? (const void *)match_volume_px_kernel<ct, kDot> : (const void *)match_volume_px_kernel<ct, kFma>))
+    const void *kfn = pr.CT == 4 ? DM_PICKX(4) : (pr.CT == 10 ? DM_PICKX(10) : DM_PICKX(16));
+#undef DM_PICKX
+    DM_CHECK(ensure_func_smem(ctx, kfn, px_smem));
+    const int grid = X.units < ctx->num_sms ? X.units : ctx->num_sms;
+    void *args[] = {(void *)&pxmap, (void *)&pxnb, (void *)&Q, (void *)&X};
+    DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kPxThreads), args, px_smem, ctx->stream));
+    count_launch(ctx);
+    return DM_OK;
+  };
   prof_begin(ctx);
   if (dot) {
     VolumeParams Pd = P;
     Pd.g = gdot;
     Pd.stats = P.stats = stats;
     Pd.dot_limit = P.dot_limit = dot_limit;
-    DM_CHECK(launch_vol(Pd, nbmap, kDot));
-    DM_CHECK(launch_vol(P, pr.tmap, kFma));
+    if (strip) {
+      DM_CHECK(launch_px(Pd, kDot));
+      DM_CHECK(launch_px(P, kFma));
+    } else {
+      DM_CHECK(launch_vol(Pd, nbmap, kDot));
+      DM_CHECK(launch_vol(P, pr.tmap, kFma));
+    }
+  } else if (strip) {
+    DM_CHECK(launch_px(P, exact ? kExact : kFma));
   } else {
     DM_CHECK(launch_vol(P, pr.tmap, exact ? kExact : kFma));
   }

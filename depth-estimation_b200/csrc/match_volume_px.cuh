@@ -1,0 +1,323 @@
+// match_volume_px.cuh -- volume mode through whole-pixel streams ("strip kernel").
+//
+// The volume [N][H1][W1][maxh*maxw] (the nn.SpatialMatching output layout,
+// /root/reference/opticalflow_model.lua:61-66 builds the module, :153-169 reads the volume) gives
+// every pixel one contiguous stream of K = maxh*maxw floats, and the streams of the pixels of an
+// image row follow each other: 16 pixels of a row are ONE contiguous run of 16*K floats, 16-byte
+// aligned when the first pixel index is a multiple of 4.  The tiled sweep (VolumeEpi) produces 8
+// entries of 128 different streams per block and has to push them out sector by sector through
+// the LSU (128 store wavefronts per block: the kernel is L1TEX-bound at 37 % of HBM).  This
+// kernel turns the loops around:
+//
+//   * a CTA walks DOWN a strip of 16 pixel columns; a step = one output row of the strip = the
+//     complete streams of 16 pixels, staged in shared memory in exactly the global layout and
+//     written by the copy engine of the SM with ONE bulk copy per step
+//     (cp.async.bulk.global.shared::cta): no store instruction, no partial sector, ever;
+//   * frame-2 rows live in a ring of maxh + 3 slots ([C][48 columns] each, one TMA box per step),
+//     so a step reads 1.9 KB of new input for 70 KB of output;
+//   * the work of a step is cut into warp items: 4 window rows x 2 displacement blocks x 4 pixel
+//     quads = 32 lanes, each lane the usual 4-pixel x 8-displacement register block
+//     (dot_block2 / ssd_block2 of match_kernels.cuh).  The lane order makes both shared-memory
+//     sides conflict-free: a quarter-warp reads blocks b and b+2 of one slab row (128 contiguous
+//     bytes per LDS.128 wavefront), and the 32 lanes of a scalar staging store hit 32 different
+//     banks (bank = 4*quad + row + 16*(which block) when K % 32 == 1 and maxw % 32 == 1, the
+//     33x33 window);
+//   * items are dealt round-robin over the compute warps ACROSS steps, the two staging buffers
+//     are handed over by mbarriers (no CTA-wide barrier): a warp that finishes its share of step
+//     s starts on step s+1 while the copy engine drains step s-1.
+//
+// Same arithmetic as the tiled kernels (the same block functions in the same order per entry), so
+// the two kernels agree bit for bit; tests/test_gpu_parity.py compares both with the oracle.
+#pragma once
+
+#include "match_kernels.cuh"
+
+namespace dm {
+
+constexpr int kPxW = 16;                           // pixels of a strip (4 quads of kP)
+constexpr int kPxWarps = 8;                        // compute warps
+constexpr int kPxThreads = (kPxWarps + 2) * 32;    // + TMA loader warp + store warp
+constexpr int kPxAhead = 3;                        // ring slots beyond the window height
+constexpr int kPxMaxSlot = 72;                     // barrier array size
+constexpr int kPxARing = 4;                        // steps of frame-1 values in flight (= kPxAhead + 1)
+
+struct PxGeom {
+  int WBs;      // slab columns a step reads: 12 + 8*n8 + (wide tail ? 12 : 4)
+  int pitch;    // floats between ring slots (multiple of 32)
+  int nb_off;   // kDot: offset of the |b|^2 row inside a slot
+  int nslot;    // maxh + kPxAhead
+  int strips, band, nbands, units;
+  int nwide;    // full-width blocks per window row (n8 + wide tail)
+  int nbp;      // block pairs per window row
+  int ndg;      // groups of four window rows
+  int nfull;    // ndg * nbp: items of full-width blocks per step
+  int items;    // nfull + items of narrow tail blocks (8 window rows each)
+};
+
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// the two blocks of pair j of a window row: (b, b + 2) inside complete groups of four blocks, what
+// is left over in a last incomplete group as it comes.  -1 = no block.
+__device__ __forceinline__ void px_block_pair(int j, int nwide, int *b0, int *b1) {
+  const int g4 = j >> 1, l = j & 1, base = 4 * g4, rem = nwide - base;
+  if (rem >= 4) {
+    *b0 = base + l;
+    *b1 = base + l + 2;
+  } else if (rem == 3) {
+    *b0 = base + l;
+    *b1 = l == 0 ? base + 2 : -1;
+  } else if (rem == 2) {
+    *b0 = base;
+    *b1 = base + 1;
+  } else {
+    *b0 = base;
+    *b1 = -1;
+  }
+}
+
+template <int CT, int MODE>
+__global__ void __launch_bounds__(kPxThreads, 1)
+match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_nb,
+                       const VolumeParams P, const PxGeom X) {
+  if (P.stats) {  // twin launch: the norm bound picks the dot or the difference form
+    const bool dot_ok = __uint_as_float(P.stats[0]) + __uint_as_float(P.stats[1]) <= P.dot_limit;
+    if (dot_ok != (MODE == kDot)) return;
+  }
+  constexpr bool EXACT = MODE == kExact;
+  const SweepGeom &g = P.g;
+  const int maxh = g.maxh, maxw = g.maxw, K = maxh * maxw;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *ring = reinterpret_cast<float *>(smem_raw);
+  float *stage = ring + (size_t)X.nslot * X.pitch;                 // [2][kPxW * K], global layout
+  // frame-1 side of a step: [CT][16] values (times -2 in the dot form), then 16 x min*log2e, 16 x 1/sum
+  constexpr int kAFloats = CT * kPxW + 2 * kPxW;
+  float *aring = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(stage + 2 * (size_t)kPxW * K) + 15) & ~uintptr_t(15));
+  uint64_t *full = reinterpret_cast<uint64_t *>(aring + kPxARing * kAFloats);
+  uint64_t *empty = full + kPxMaxSlot, *sdone = empty + kPxMaxSlot, *sfree = sdone + 2, *afull = sfree + 2;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap);
+    if (MODE == kDot) prefetch_tmap(&tmap_nb);
+    for (int s = 0; s < X.nslot; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kPxWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sdone[b], kPxWarps);
+      mbar_init(&sfree[b], 1);
+    }
+    for (int b = 0; b < kPxARing; ++b) mbar_init(&afull[b], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const uint32_t slab_bytes = (uint32_t)((CT + (MODE == kDot ? 1 : 0)) * X.WBs * sizeof(float));
+  uint32_t rbase = 0, sbase = 0;   // rows / steps of the units before this one (all roles count alike)
+  for (int unit = blockIdx.x; unit < X.units; unit += gridDim.x) {
+    int u = unit;
+    const int yb = u % X.nbands; u /= X.nbands;
+    const int xs = u % X.strips;
+    const int n = u / X.strips;
+    const int y0 = yb * X.band, y1 = min(g.H1, y0 + X.band);
+    const int steps = y1 - y0, rows = steps + maxh - 1;
+    const int x0 = xs * kPxW;
+
+    if (warp == kPxWarps) {
+      // ---------------- loader: frame-2 row y0 + j -> slot (rbase + j) % nslot (TMA, lane 0), and the
+      // frame-1 values of the step that needs this row first, t = j - (maxh - 1), into the a-ring (all
+      // lanes, plain loads: frame 1 may have any strides).  The wait on the row's slot also covers the
+      // a-ring: the previous tenant of the slot is row j - nslot, released after step t - kPxARing.
+      for (int j = 0; j < rows; ++j) {
+        const uint32_t seq = rbase + (uint32_t)j;
+        const int slot = (int)(seq % (uint32_t)X.nslot);
+        const uint32_t inst = seq / (uint32_t)X.nslot;
+        if (lane == 0) {
+          if (inst > 0) mbar_wait_backoff(&empty[slot], (inst - 1) & 1u);
+          mbar_arrive_expect_tx(&full[slot], slab_bytes);
+          tma_load_4d(ring + (size_t)slot * X.pitch, &tmap, &full[slot], x0, y0 + j, 0, n);
+          if (MODE == kDot) tma_load_4d(ring + (size_t)slot * X.pitch + X.nb_off, &tmap_nb, &full[slot], x0, y0 + j, 0, n);
+        }
+        __syncwarp();
+        const int t = j - (maxh - 1);
+        if (t >= 0) {
+          const uint32_t sg = sbase + (uint32_t)t;
+          float *dst = aring + (sg % kPxARing) * kAFloats;
+          const int y = y0 + t;
+          const float *src = g.in1 + (long long)n * g.s1n + (long long)y * g.s1y;
+          const size_t orow = ((size_t)n * g.H1 + y) * g.W1;
+          float v[(kAFloats + 31) / 32];
+#pragma unroll
+          for (int e = 0; e < (kAFloats + 31) / 32; ++e) {
+            const int idx = lane + 32 * e, k = idx / kPxW, x = x0 + (idx % kPxW);
+            float t0 = 0.0f;
+            if (idx < CT * kPxW) {
+              if (k < g.Cin && x < g.W1) t0 = __ldg(src + (long long)k * g.s1c + x) * (MODE == kDot ? -2.0f : 1.0f);
+            } else if (idx < kAFloats) {
+              const bool second = idx >= CT * kPxW + kPxW;
+              t0 = second ? 1.0f : 0.0f;
+              if (P.mode == DM_VOLUME_NEG_SOFTMAX && x < g.W1)
+                t0 = second ? __ldg(P.vinv + orow + x) : __ldg(P.vmin + orow + x) * kLog2e;
+            }
+            v[e] = t0;
+          }
+#pragma unroll
+          for (int e = 0; e < (kAFloats + 31) / 32; ++e)
+            if (lane + 32 * e < kAFloats) dst[lane + 32 * e] = v[e];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&afull[sg % kPxARing]);
+        }
+      }
+    } else if (warp == kPxWarps + 1) {
+      // ---------------- store warp: one bulk copy per step, the streams of the strip's pixels
+      if (lane == 0) {
+        const int npx = min(kPxW, g.W1 - x0);
+        const uint32_t bytes = (uint32_t)((size_t)npx * K * sizeof(float));
+        for (int s = 0; s < steps; ++s) {
+          const uint32_t sg = sbase + (uint32_t)s, b = sg & 1u, use = sg >> 1;
+          mbar_wait_backoff(&sdone[b], use & 1u);
+          float *dst = P.out + (((size_t)n * g.H1 + (y0 + s)) * g.W1 + x0) * (size_t)K;
+          if (P.debug != 1) {
+            bulk_store(dst, stage + (size_t)b * kPxW * K, bytes);
+            bulk_commit();
+            bulk_wait_read0();               // the copy engine has read the buffer
+          }
+          mbar_arrive(&sfree[b]);
+        }
+      }
+    } else {
+      // ---------------- compute warps
+      const int q = lane & 3, sl = lane >> 2, ddy = sl >> 1, hb = sl & 1;
+      for (int s = 0; s < steps; ++s) {
+        const uint32_t sg = sbase + (uint32_t)s, b = sg & 1u, use = sg >> 1;
+        const int y = y0 + s;
+        // every warp observes every row's arrival once, in order
+        if (s == 0) {
+          for (int j = 0; j < maxh - 1; ++j) {
+            const uint32_t seq = rbase + (uint32_t)j;
+            mbar_wait(&full[seq % (uint32_t)X.nslot], (seq / (uint32_t)X.nslot) & 1u);
+          }
+        }
+        {
+          const uint32_t seq = rbase + (uint32_t)(s + maxh - 1);
+          mbar_wait(&full[seq % (uint32_t)X.nslot], (seq / (uint32_t)X.nslot) & 1u);
+        }
+        // the copy engine is done with this step's staging buffer.  EVERY warp waits, also one without
+        // items in this step: its arrival on sdone must not run a phase ahead of the slowest warp
+        if (use > 0) mbar_wait(&sfree[b], (use - 1) & 1u);
+        const int rs = (int)((rbase + (uint32_t)s) % (uint32_t)X.nslot);   // slot of window row 0
+        // this warp's items of the step: global item number sg * items + i, dealt round robin
+        const int i0 = (int)(((uint32_t)warp + kPxWarps - (uint32_t)(((unsigned long long)sg * (unsigned)X.items) % kPxWarps)) % kPxWarps);
+        if (i0 < X.items) {
+          float2 a2[CT][2];
+          float mL[kP], inv[kP];
+          {
+            mbar_wait(&afull[sg % kPxARing], (sg / kPxARing) & 1u);
+            const float4 *src = reinterpret_cast<const float4 *>(aring + (sg % kPxARing) * kAFloats) + q;
+#pragma unroll
+            for (int k = 0; k < CT; ++k) {
+              const float4 a = src[k * (kPxW / 4)];
+              a2[k][0] = make_float2(a.x, a.y);
+              a2[k][1] = make_float2(a.z, a.w);
+            }
+            const float4 m4 = src[CT * (kPxW / 4)], i4 = src[(CT + 1) * (kPxW / 4)];
+            mL[0] = m4.x, mL[1] = m4.y, mL[2] = m4.z, mL[3] = m4.w;
+            inv[0] = i4.x, inv[1] = i4.y, inv[2] = i4.z, inv[3] = i4.w;
+          }
+          float *stg = stage + (size_t)b * kPxW * K + (size_t)(q * kP) * K;
+          for (int i = i0; i < X.items; i += kPxWarps) {
+            if (i < X.nfull) {
+              const int dg = i / X.nbp, j = i - dg * X.nbp;
+              int b0, b1;
+              px_block_pair(j, X.nwide, &b0, &b1);
+              const int dy = 4 * dg + ddy, blk = hb ? b1 : b0;
+              const bool active = dy < maxh && blk >= 0;
+              int slot = rs + (active ? dy : 0);
+              slot -= slot >= X.nslot ? X.nslot : 0;
+              const float *brow = ring + (size_t)slot * X.pitch + q * kP + (active ? blk : 0) * kR;
+              float2 acc2[2][kR];
+              if constexpr (MODE == kDot)
+                dot_block2<CT, kR>(a2, brow, brow + X.nb_off, X.WBs, acc2);
+              else
+                ssd_block2<CT, EXACT, kR>(a2, brow, X.WBs, acc2);
+              float acc[kP][kR];
+              unpack_block<kR>(acc2, acc);
+              if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
+#pragma unroll
+                for (int p = 0; p < kP; ++p)
+#pragma unroll
+                  for (int r = 0; r < kR; ++r) acc[p][r] = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p])) * inv[p];
+              }
+              if (active) {
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                  float *dst = stg + p * K + dy * maxw + blk * kR - (p & 1);
+#pragma unroll
+                  for (int r = 0; r < kR; ++r) {
+                    const int dx = blk * kR - (p & 1) + r;
+                    if (dx >= 0 && dx < maxw) dst[r] = acc[p][r];
+                  }
+                }
+              }
+            } else {
+              // narrow tail blocks (2 columns): 8 window rows x 4 quads
+              const int dy = 8 * (i - X.nfull) + sl, blk = g.bs.n8;
+              const bool active = dy < maxh;
+              int slot = rs + (active ? dy : 0);
+              slot -= slot >= X.nslot ? X.nslot : 0;
+              const float *brow = ring + (size_t)slot * X.pitch + q * kP + blk * kR;
+              float2 acc2[2][2];
+              if constexpr (MODE == kDot)
+                dot_block2<CT, 2>(a2, brow, brow + X.nb_off, X.WBs, acc2);
+              else
+                ssd_block2<CT, EXACT, 2>(a2, brow, X.WBs, acc2);
+              float acc[kP][2];
+              unpack_block<2>(acc2, acc);
+              if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
+#pragma unroll
+                for (int p = 0; p < kP; ++p)
+#pragma unroll
+                  for (int r = 0; r < 2; ++r) acc[p][r] = ex2_approx(fmaf(acc[p][r], -kLog2e, mL[p])) * inv[p];
+              }
+              if (active) {
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                  float *dst = stg + p * K + dy * maxw + blk * kR - (p & 1);
+#pragma unroll
+                  for (int r = 0; r < 2; ++r) {
+                    const int dx = blk * kR - (p & 1) + r;
+                    if (dx >= 0 && dx < maxw) dst[r] = acc[p][r];
+                  }
+                }
+              }
+            }
+          }
+          fence_proxy_async();   // the staging stores of this thread -> visible to the copy engine
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sdone[b]);
+          // window row 0 of this step is not read again; the last step releases the rest
+          mbar_arrive(&empty[rs]);
+          if (s == steps - 1)
+            for (int j = 1; j < maxh; ++j) {
+              int slot = rs + j;
+              slot -= slot >= X.nslot ? X.nslot : 0;
+              mbar_arrive(&empty[slot]);
+            }
+        }
+      }
+    }
+    rbase += (uint32_t)rows;
+    sbase += (uint32_t)steps;
+  }
+  if (warp == kPxWarps + 1 && lane == 0) bulk_wait0();   // global writes complete before the CTA retires
+}
+
+}  // namespace dm

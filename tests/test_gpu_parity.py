@@ -170,6 +170,47 @@ def test_volume_ssd_and_softmax_vs_oracle(dm, oracle, case):
     np.testing.assert_allclose(out, prob, rtol=1e-5, atol=1e-12)
 
 
+@pytest.mark.parametrize("case", [(10, 30, 152, 9, 17), (4, 12, 100, 5, 33), (10, 20, 71, 8, 8), (16, 40, 64, 33, 33),
+                                  (3, 26, 44, 17, 9), (10, 21, 40, 4, 25)])
+def test_volume_strip_kernel_vs_oracle_and_tiled_kernel(dm, oracle, case):
+    """W1 % 4 == 0: the strip kernel (whole pixel streams, bulk copies; match_volume_px.cuh).  Against the
+    oracle, and bit for bit against the tiled kernel (option volume_kernel = 1)."""
+    C, H2, W2, maxh, maxw = case
+    in1, in2, _ = make_pair(C, H2, W2, maxh, maxw, seed=5, noise=0.5)
+    assert in1.shape[2] % 4 == 0
+    vol = oracle.spatial_matching(in1, in2, maxh, maxw)
+    prob = oracle.neg_softmax(vol)
+    ctx = dm.default_context()
+    res = {}
+    for kern in (0, 1):
+        ctx.set_option("volume_kernel", kern)
+        res[kern] = (dm.match_volume(in1, in2, maxh, maxw, exact=True), dm.match_volume(in1, in2, maxh, maxw),
+                     dm.match_volume(in1, in2, maxh, maxw, softmax=True))
+    ctx.set_option("volume_kernel", 0)
+    np.testing.assert_array_equal(res[0][0], vol)
+    np.testing.assert_allclose(res[0][1], vol, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(res[0][2], prob, rtol=RTOL, atol=1e-9)
+    for a, b in zip(res[0], res[1]):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_volume_strip_kernel_many_units_per_cta(dm, oracle):
+    """More units than SMs (barrier phases carried across units), a partial last strip and row bands."""
+    import torch
+    rng = np.random.default_rng(11)
+    N, C, maxh, maxw = 5, 10, 9, 9
+    H1, W1 = 45, 168
+    in2 = rng.standard_normal((N, C, H1 + maxh - 1, W1 + maxw - 1), dtype=np.float32)
+    in1 = (in2[:, :, 4:4 + H1, 3:3 + W1] + 0.3 * rng.standard_normal((N, C, H1, W1), dtype=np.float32)).copy()
+    t1, t2 = torch.from_numpy(in1).cuda(), torch.from_numpy(in2).cuda()
+    got = dm.match_volume(t1, t2, maxh, maxw, exact=True).cpu().numpy()
+    gotp = dm.match_volume(t1, t2, maxh, maxw, softmax=True).cpu().numpy()
+    for n in range(N):
+        vol = oracle.spatial_matching(in1[n], in2[n], maxh, maxw)
+        np.testing.assert_array_equal(got[n], vol)
+        np.testing.assert_allclose(gotp[n], oracle.neg_softmax(vol), rtol=RTOL, atol=1e-9)
+
+
 def test_module_level_process_output_vs_oracle(dm, oracle):
     """getModel(prefiltered) -> forward -> processOutput for 'max', 'max'+threshold and 'mean'."""
     maxh, maxw = 9, 9
