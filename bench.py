@@ -539,7 +539,18 @@ def main():
         va = BYTES_VOLUME * Bv / (vms / 1e3) / 1e9
         line["volume_mode"] = {"value": Bv / (vms / 1e3), "unit": "frame-pairs/s", "kernel_ms": vms,
                                "roofline": {"bound": "hbm", "achieved": va, "peak": hbm_gbs, "unit": "GB/s",
-                                            "frac": va / hbm_gbs, "kernel": "match_volume_kernel<10>"}}
+                                            "frac": va / hbm_gbs, "kernel": "match_volume_px_kernel<10, kFma>",
+                                            "traffic": 834.8e6, "traffic_unit": "bytes per pair (810.6 MB written + 24.3 MB read)",
+                                            "traffic_source": "profiles/r02_ncu_volume_strip.md", "algorithmic_bytes": BYTES_VOLUME}}
+        # the round-1 kernel (sector stores from the tiled sweep), for the record
+        ctx.set_option("volume_kernel", 1)
+        vs1 = []
+        for _ in range(3):
+            dm.match_volume(v1, v2, MAXH, MAXW, ctx=ctx)
+            vs1.append(ctx.last_kernel_ms())
+        torch.cuda.synchronize()
+        ctx.set_option("volume_kernel", 0)
+        line["volume_mode"]["tiled_kernel_ms"] = float(np.mean(vs1[1:]))
         # the same with the Minus + SoftMax stages (what the reference's model:forward returns):
         # statistics sweep + volume sweep, timed with CUDA events around the call
         import ctypes

@@ -1461,13 +1461,22 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     X.nwide = bs.n8 + (wide ? 1 : 0);
     const int rem = X.nwide % 4;
     X.nbp = 2 * (X.nwide / 4) + (rem + 1) / 2;
-    X.ndg = (maxh + 3) / 4;
+    // window rows in groups of four; one or two rows left over by a four-block-wide window (33 = 8 * 4 + 1)
+    // are one item of their own instead of a mostly idle group
+    X.nrow = (X.nwide == 4 && maxh >= 4 && (maxh % 4 == 1 || maxh % 4 == 2)) ? 1 : 0;
+    X.ndg = X.nrow ? maxh / 4 : (maxh + 3) / 4;
     X.nfull = X.ndg * X.nbp;
-    X.items = X.nfull + (wide ? 0 : (maxh + 7) / 8);
+    X.items = X.nfull + X.nrow + (wide ? 0 : (maxh + 7) / 8);
     X.strips = (g.W1 + kPxW - 1) / kPxW;
+    X.ncw = kPxMaxWarps;
+    {
+      auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+      X.rot = X.items;
+      while (gcd(X.rot, X.ncw) != 1) ++X.rot;
+    }
     px_smem = ((size_t)X.nslot * X.pitch + 2 * (size_t)kPxW * K + 4 + (size_t)kPxARing * (pr.CT * kPxW + 2 * kPxW)) * sizeof(float) +
               (2 * kPxMaxSlot + 4 + kPxARing) * sizeof(uint64_t);
-    strip = X.WBs <= 256 && X.nslot <= kPxMaxSlot && X.nwide >= 1 && px_smem <= ctx->smem_optin;
+    strip = strip && X.WBs <= 256 && X.nslot <= kPxMaxSlot && X.nwide >= 1 && px_smem <= ctx->smem_optin;
   }
   if (strip) {
     // rows per unit: the split of the strips into row bands that fills the CTAs' waves best (a unit
@@ -1507,7 +1516,7 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     DM_CHECK(ensure_func_smem(ctx, kfn, px_smem));
     const int grid = X.units < ctx->num_sms ? X.units : ctx->num_sms;
     void *args[] = {(void *)&pxmap, (void *)&pxnb, (void *)&Q, (void *)&X};
-    DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3(kPxThreads), args, px_smem, ctx->stream));
+    DM_CUDA(cudaLaunchKernel(kfn, dim3(grid), dim3((X.ncw + 2) * 32), args, px_smem, ctx->stream));
     count_launch(ctx);
     return DM_OK;
   };

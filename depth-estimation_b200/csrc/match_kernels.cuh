@@ -98,7 +98,7 @@ enum SsdMode { kFma = 0, kExact = 1, kDot = 2 };
 template <int CT, int JW>
 __device__ __forceinline__ void dot_block2(const float2 (&a2)[CT][2], const float *bsrc, const float *nbsrc, int WB,
                                            float2 (&acc2)[2][JW]) {
-  constexpr int NBF = JW == kR ? kNB : kP;
+  constexpr int NBF = JW == 2 ? kP : JW + kP;   // slab floats a block reads per channel: 4 (tail), 12, 20
   float nb[NBF];
   {
     const float4 *src = reinterpret_cast<const float4 *>(nbsrc);
@@ -143,7 +143,7 @@ __device__ __forceinline__ void dot_block2(const float2 (&a2)[CT][2], const floa
 template <int CT, bool EXACT, int JW>
 __device__ __forceinline__ void ssd_block2(const float2 (&a2)[CT][2], const float *bsrc, int WB,
                                            float2 (&acc2)[2][JW]) {
-  constexpr int NBF = JW == kR ? kNB : kP;
+  constexpr int NBF = JW == 2 ? kP : JW + kP;   // slab floats a block reads per channel: 4 (tail), 12, 20
 #pragma unroll
   for (int k = 0; k < CT; ++k) {
     float b[NBF];

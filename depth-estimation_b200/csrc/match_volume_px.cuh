@@ -22,9 +22,11 @@
 //     bytes per LDS.128 wavefront), and the 32 lanes of a scalar staging store hit 32 different
 //     banks (bank = 4*quad + row + 16*(which block) when K % 32 == 1 and maxw % 32 == 1, the
 //     33x33 window);
-//   * items are dealt round-robin over the compute warps ACROSS steps, the two staging buffers
-//     are handed over by mbarriers (no CTA-wide barrier): a warp that finishes its share of step
-//     s starts on step s+1 while the copy engine drains step s-1.
+//   * items are dealt round-robin over the compute warps ACROSS steps (measured: a fixed, per-warp
+//     balanced assignment is 28 % slower -- what has to balance is the load per SM sub-partition,
+//     and the rotation does that for free); the two staging buffers are handed over by mbarriers
+//     (no CTA-wide barrier): a warp that finishes its share of step s starts on step s+1 while the
+//     copy engine drains step s-1.
 //
 // Same arithmetic as the tiled kernels (the same block functions in the same order per entry), so
 // the two kernels agree bit for bit; tests/test_gpu_parity.py compares both with the oracle.
@@ -35,8 +37,8 @@
 namespace dm {
 
 constexpr int kPxW = 16;                           // pixels of a strip (4 quads of kP)
-constexpr int kPxWarps = 8;                        // compute warps
-constexpr int kPxThreads = (kPxWarps + 2) * 32;    // + TMA loader warp + store warp
+constexpr int kPxMaxWarps = 8;                     // compute warps (6 / 10 / 12 / 14 measured: 0.39 / 0.31 / 0.30 / 0.30 ms against 0.29)
+constexpr int kPxMaxThreads = (kPxMaxWarps + 2) * 32;   // + TMA loader warp + store warp
 constexpr int kPxAhead = 3;                        // ring slots beyond the window height
 constexpr int kPxMaxSlot = 72;                     // barrier array size
 constexpr int kPxARing = 4;                        // steps of frame-1 values in flight (= kPxAhead + 1)
@@ -52,6 +54,9 @@ struct PxGeom {
   int ndg;      // groups of four window rows
   int nfull;    // ndg * nbp: items of full-width blocks per step
   int items;    // nfull + items of narrow tail blocks (8 window rows each)
+  int ncw;      // compute warps
+  int rot;      // rotation of the item deal per step (>= items, coprime to ncw)
+  int nrow;     // 1: the maxh % 4 (1 or 2) rows left over are one item of their own (four blocks wide)
 };
 
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
@@ -82,7 +87,7 @@ __device__ __forceinline__ void px_block_pair(int j, int nwide, int *b0, int *b1
 }
 
 template <int CT, int MODE>
-__global__ void __launch_bounds__(kPxThreads, 1)
+__global__ void __launch_bounds__(kPxMaxThreads, 1)
 match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_nb,
                        const VolumeParams P, const PxGeom X) {
   if (P.stats) {  // twin launch: the norm bound picks the dot or the difference form
@@ -101,6 +106,7 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   uint64_t *full = reinterpret_cast<uint64_t *>(aring + kPxARing * kAFloats);
   uint64_t *empty = full + kPxMaxSlot, *sdone = empty + kPxMaxSlot, *sfree = sdone + 2, *afull = sfree + 2;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  constexpr int kPxWarps = kPxMaxWarps;   // compile-time: the item rotation and barrier counts fold
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap);
@@ -138,21 +144,13 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         const uint32_t seq = rbase + (uint32_t)j;
         const int slot = (int)(seq % (uint32_t)X.nslot);
         const uint32_t inst = seq / (uint32_t)X.nslot;
-        if (lane == 0) {
-          if (inst > 0) mbar_wait_backoff(&empty[slot], (inst - 1) & 1u);
-          mbar_arrive_expect_tx(&full[slot], slab_bytes);
-          tma_load_4d(ring + (size_t)slot * X.pitch, &tmap, &full[slot], x0, y0 + j, 0, n);
-          if (MODE == kDot) tma_load_4d(ring + (size_t)slot * X.pitch + X.nb_off, &tmap_nb, &full[slot], x0, y0 + j, 0, n);
-        }
-        __syncwarp();
+        // frame-1 values first: the loads do not depend on the slot, their latency passes under the wait
         const int t = j - (maxh - 1);
+        float v[(kAFloats + 31) / 32];
         if (t >= 0) {
-          const uint32_t sg = sbase + (uint32_t)t;
-          float *dst = aring + (sg % kPxARing) * kAFloats;
           const int y = y0 + t;
           const float *src = g.in1 + (long long)n * g.s1n + (long long)y * g.s1y;
           const size_t orow = ((size_t)n * g.H1 + y) * g.W1;
-          float v[(kAFloats + 31) / 32];
 #pragma unroll
           for (int e = 0; e < (kAFloats + 31) / 32; ++e) {
             const int idx = lane + 32 * e, k = idx / kPxW, x = x0 + (idx % kPxW);
@@ -167,6 +165,17 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             }
             v[e] = t0;
           }
+        }
+        if (lane == 0) {
+          if (inst > 0) mbar_wait_backoff(&empty[slot], (inst - 1) & 1u);
+          mbar_arrive_expect_tx(&full[slot], slab_bytes);
+          tma_load_4d(ring + (size_t)slot * X.pitch, &tmap, &full[slot], x0, y0 + j, 0, n);
+          if (MODE == kDot) tma_load_4d(ring + (size_t)slot * X.pitch + X.nb_off, &tmap_nb, &full[slot], x0, y0 + j, 0, n);
+        }
+        __syncwarp();
+        if (t >= 0) {
+          const uint32_t sg = sbase + (uint32_t)t;
+          float *dst = aring + (sg % kPxARing) * kAFloats;
 #pragma unroll
           for (int e = 0; e < (kAFloats + 31) / 32; ++e)
             if (lane + 32 * e < kAFloats) dst[lane + 32 * e] = v[e];
@@ -183,7 +192,7 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
           const uint32_t sg = sbase + (uint32_t)s, b = sg & 1u, use = sg >> 1;
           mbar_wait_backoff(&sdone[b], use & 1u);
           float *dst = P.out + (((size_t)n * g.H1 + (y0 + s)) * g.W1 + x0) * (size_t)K;
-          if (P.debug != 1) {
+          if (!(P.debug & 1)) {
             bulk_store(dst, stage + (size_t)b * kPxW * K, bytes);
             bulk_commit();
             bulk_wait_read0();               // the copy engine has read the buffer
@@ -212,8 +221,10 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
         // items in this step: its arrival on sdone must not run a phase ahead of the slowest warp
         if (use > 0) mbar_wait(&sfree[b], (use - 1) & 1u);
         const int rs = (int)((rbase + (uint32_t)s) % (uint32_t)X.nslot);   // slot of window row 0
-        // this warp's items of the step: global item number sg * items + i, dealt round robin
-        const int i0 = (int)(((uint32_t)warp + kPxWarps - (uint32_t)(((unsigned long long)sg * (unsigned)X.items) % kPxWarps)) % kPxWarps);
+        // this warp's items of the step: item i of step sg goes to warp (sg * rot + i) % warps.  rot >= items
+        // is coprime to the warp count, so every warp meets every residue in turn: with rot = 22 and 8
+        // warps the even warps kept the heavier residues and two SM sub-partitions ran 12 % longer
+        const int i0 = (int)(((uint32_t)warp + kPxWarps - (uint32_t)(((unsigned long long)sg * (unsigned)X.rot) % kPxWarps)) % kPxWarps);
         if (i0 < X.items) {
           float2 a2[CT][2];
           float mL[kP], inv[kP];
@@ -232,15 +243,23 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
           }
           float *stg = stage + (size_t)b * kPxW * K + (size_t)(q * kP) * K;
           for (int i = i0; i < X.items; i += kPxWarps) {
-            if (i < X.nfull) {
-              const int dg = i / X.nbp, j = i - dg * X.nbp;
-              int b0, b1;
-              px_block_pair(j, X.nwide, &b0, &b1);
-              const int dy = 4 * dg + ddy, blk = hb ? b1 : b0;
+            if (i < X.nfull + X.nrow) {
+              int dy, blk;
+              if (i < X.nfull) {   // four window rows x a pair of blocks
+                const int dg = i / X.nbp, j = i - dg * X.nbp;
+                int b0, b1;
+                px_block_pair(j, X.nwide, &b0, &b1);
+                dy = 4 * dg + ddy;
+                blk = hb ? b1 : b0;
+              } else {             // the one or two window rows left over by the groups of four x four blocks
+                dy = 4 * X.ndg + (sl >> 2);
+                blk = (sl & 1) * 2 + ((sl >> 1) & 1);
+              }
               const bool active = dy < maxh && blk >= 0;
               int slot = rs + (active ? dy : 0);
               slot -= slot >= X.nslot ? X.nslot : 0;
-              const float *brow = ring + (size_t)slot * X.pitch + q * kP + (active ? blk : 0) * kR;
+              const int dx0 = (active ? blk : 0) * kR;     // first displacement of the block (even pixels)
+              const float *brow = ring + (size_t)slot * X.pitch + q * kP + dx0;
               float2 acc2[2][kR];
               if constexpr (MODE == kDot)
                 dot_block2<CT, kR>(a2, brow, brow + X.nb_off, X.WBs, acc2);
@@ -257,17 +276,17 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
               if (active) {
 #pragma unroll
                 for (int p = 0; p < kP; ++p) {
-                  float *dst = stg + p * K + dy * maxw + blk * kR - (p & 1);
+                  float *dst = stg + p * K + dy * maxw + dx0 - (p & 1);
 #pragma unroll
                   for (int r = 0; r < kR; ++r) {
-                    const int dx = blk * kR - (p & 1) + r;
+                    const int dx = dx0 - (p & 1) + r;
                     if (dx >= 0 && dx < maxw) dst[r] = acc[p][r];
                   }
                 }
               }
             } else {
               // narrow tail blocks (2 columns): 8 window rows x 4 quads
-              const int dy = 8 * (i - X.nfull) + sl, blk = g.bs.n8;
+              const int dy = 8 * (i - X.nfull - X.nrow) + sl, blk = g.bs.n8;
               const bool active = dy < maxh;
               int slot = rs + (active ? dy : 0);
               slot -= slot >= X.nslot ? X.nslot : 0;
