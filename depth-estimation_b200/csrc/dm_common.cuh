@@ -59,7 +59,7 @@ struct Options {
   int pipe_chunk = 0, volume_debug = 0;
   int conv_tile = 0, conv_target = 0;
   int sweep = 0;     // 0 auto; other values select a sweep variant (tuning)
-  int volume_kernel = 0;  // 0 auto (strip kernel where it fits), 1 = tiled kernel with sector stores
+  int volume_kernel = 0;  // 0 auto (strip kernel where it fits and pays), 1 = tiled kernel with sector stores, 2 = strip kernel wherever it fits
   int conv = 0;      // feature extractor: 2 = tensor-core (tcgen05) layers where they fit; else CUDA cores
 };
 }  // namespace dm

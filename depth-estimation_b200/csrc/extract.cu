@@ -11,7 +11,7 @@ constexpr int kRowWarps = 8;
 
 __device__ __forceinline__ long long warp_row(long long rows) {
   (void)rows;
-  return (long long)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  return (long long)blockIdx.x * kRowWarps + __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
 }
 
 // nn.Minus + nn.SoftMax (opticalflow_model.lua:94-109)

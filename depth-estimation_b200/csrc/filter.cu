@@ -93,7 +93,7 @@ __global__ void conv_tile_kernel(const ConvArgs a) {
   const int img = blockIdx.z;
   const int ox0 = blockIdx.x * a.tw, oy0 = blockIdx.y * a.th;
   const int plane_s = a.rows * a.pitch;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // shuffle: warp-uniform for the compiler
   {  // input footprint of every plane, zero padding materialised (cp.async zero-fill); one
      // warp per row, every copy in flight before anybody waits
     const float *src = a.in + (size_t)img * a.n_in * a.h * a.w;

@@ -1477,6 +1477,9 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     px_smem = ((size_t)X.nslot * X.pitch + 2 * (size_t)kPxW * K + 4 + (size_t)kPxARing * (pr.CT * kPxW + 2 * kPxW)) * sizeof(float) +
               (2 * kPxMaxSlot + 4 + kPxARing) * sizeof(uint64_t);
     strip = strip && X.WBs <= 256 && X.nslot <= kPxMaxSlot && X.nwide >= 1 && px_smem <= ctx->smem_optin;
+    // a step must hold enough items to keep the warps busy between two hand-overs: small windows (the
+    // multiscale 8x8: 3 items per step, measured 0.38 against 0.33 ms) stay with the tiled kernel
+    if (X.items < 2 * kPxMaxWarps && ctx->opt.volume_kernel != 2) strip = false;
   }
   if (strip) {
     // rows per unit: the split of the strips into row bands that fills the CTAs' waves best (a unit

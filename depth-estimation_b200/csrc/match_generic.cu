@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kGWarps * 32) generic_kernel(const GenericPara
   const int K = P.maxh * P.maxw;
   const bool exact = P.flags & DM_FLAG_EXACT_SSD;
   const long long nwork = P.list ? (long long)*P.nlist : npx;
-  for (long long it = (long long)blockIdx.x * kGWarps + (threadIdx.x >> 5); it < nwork;
+  for (long long it = (long long)blockIdx.x * kGWarps + __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); it < nwork;
        it += (long long)gridDim.x * kGWarps) {
     const long long px = P.list ? (long long)P.list[it] : it;
     const int x = (int)(px % P.W1);

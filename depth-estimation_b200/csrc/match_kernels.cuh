@@ -202,7 +202,9 @@ __device__ __forceinline__ void run_sweep(const CUtensorMap *tmap, const CUtenso
   constexpr bool EXACT = MODE == kExact;
   constexpr int kWarps = Cfg::kWarps, kTH = Cfg::kTH;
   const int kNSlot = g.nslot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle tells the compiler that the warp index is warp-uniform: the row tests below become uniform
+  // branches and the slot arithmetic moves to the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int rows_total = kTH + g.maxh - 1;
   const uint32_t slab_bytes = (uint32_t)((g.C + (MODE == kDot ? 1 : 0)) * g.WB * sizeof(float));
   const int slab_floats = g.slab_floats;

@@ -451,7 +451,7 @@ match_sweep2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 
   constexpr int kWarps = Cfg::kWarps, kTH = Cfg::kTH;
   const int kNSlot = g.nslot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int rows_total = kTH + g.maxh - 1;
   const uint32_t slab_bytes = (uint32_t)((g.C + 1) * g.WB * sizeof(float));
   const int slab_floats = g.slab_floats;

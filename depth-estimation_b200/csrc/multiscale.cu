@@ -261,7 +261,7 @@ ring_argmax_kernel(ScaleMaps maps, const int *chain, int h, int w, int maxh, int
   // first kBatch lanes decode and store the results (coalesced 8-byte stores).  Small batches keep
   // the last wave of the grid short (a 640x360 frame is only ~2 batches of 32 per resident warp).
   constexpr int kBatch = 8;
-  for (long long px0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kBatch; px0 < npx;
+  for (long long px0 = ((long long)blockIdx.x * 8 + __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0)) * kBatch; px0 < npx;
        px0 += (long long)gridDim.x * 8 * kBatch) {
    long long mywin = 0;
    // per-scale offset of the window of pixel px0 + lane, computed by its lane (the divisions

@@ -67,12 +67,14 @@ int dm_set_profiling(dm_ctx *ctx, int on);
 int dm_last_kernel_ms(dm_ctx *ctx, float *ms);
 /* tuning / diagnostic switches (none is needed for normal use).  The environment variables
  * DM_SSD_FORM, DM_NO_SMALL_TILES, DM_NO_PIPELINE, DM_PIPE_CHUNK, DM_VOLUME_DEBUG, DM_DEBUG_TODO,
- * DM_CONV_TILE, DM_SWEEP, DM_CONV are read once, in dm_create; this changes them on a live context.  Names:
+ * DM_CONV_TILE, DM_SWEEP, DM_CONV, DM_VOLUME_KERNEL are read once, in dm_create; this changes them on a live context.  Names:
  * "ssd_form" = "auto" | "diff" | "dot"; "no_small_tiles", "no_pipeline", "debug_todo" = "0" | "1";
  * "pipe_chunk", "volume_debug", "sweep" = integer; "conv_tile" = "<candidate>,<CTAs per SM>";
  * "sweep" = 2 | 3: the two-rows-per-warp dot sweep (match_sweep2.cuh); "conv" = 2: the feature
  * extractor's layers on the tensor cores (tcgen05, filter_tc.cu).  Both variants meet the parity
- * bars and are measured slower than the defaults on B200, hence opt-in. */
+ * bars and are measured slower than the defaults on B200, hence opt-in.  "volume_kernel" = 0: volume
+ * mode picks the strip kernel (whole pixel streams written by bulk copies, match_volume_px.cuh) where it
+ * fits and pays, 1: always the tiled kernel with sector stores, 2: the strip kernel wherever it fits. */
 int dm_set_option(dm_ctx *ctx, const char *name, const char *value);
 /* the "near-tie pixels are logged" part of the parity contract: how many pixels of the most
  * recent dm_match_extract on this context were handed to the entry-by-entry rescore (window entries

@@ -55,3 +55,4 @@ def _reset_tuning_options(request):
             ctx.set_option("no_small_tiles", "0")
             ctx.set_option("sweep", "0")
             ctx.set_option("conv", "0")
+            ctx.set_option("volume_kernel", "0")
