@@ -229,6 +229,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, the image's setting) goes
+        # to stdout too, so it is switched off unless the caller asked for real NCCL logging
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -540,8 +544,9 @@ def main():
         line["volume_mode"] = {"value": Bv / (vms / 1e3), "unit": "frame-pairs/s", "kernel_ms": vms,
                                "roofline": {"bound": "hbm", "achieved": va, "peak": hbm_gbs, "unit": "GB/s",
                                             "frac": va / hbm_gbs, "kernel": "match_volume_px_kernel<10, kFma>",
-                                            "traffic": 834.8e6, "traffic_unit": "bytes per pair (810.6 MB written + 24.3 MB read)",
-                                            "traffic_source": "profiles/r02_ncu_volume_strip.md", "algorithmic_bytes": BYTES_VOLUME}}
+                                            "traffic": 1729.1e6, "traffic_unit": "bytes per launch of 2 pairs (1679.6 MB written + 49.5 MB read; "
+                                            "the last ~57 MB of the volume are still dirty in L2 when the kernel ends)",
+                                            "traffic_source": "profiles/r02_ncu_volume_strip.md, launch #16", "algorithmic_bytes": BYTES_VOLUME * Bv}}
         # the round-1 kernel (sector stores from the tiled sweep), for the record
         ctx.set_option("volume_kernel", 1)
         vs1 = []
