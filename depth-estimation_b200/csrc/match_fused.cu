@@ -1408,7 +1408,76 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     stats = static_cast<const unsigned *>(st);
     dot_limit = ctx->opt.ssd_form == 2 ? 3.0e38f : 1.0e-4f / ((float)(pr.Cin + 2) * 5.9604645e-8f);
   }
-  if (mode == DM_VOLUME_NEG_SOFTMAX) {
+  // The strip kernel (match_volume_px.cuh) writes whole pixel streams with bulk copies; it needs
+  // 16-byte aligned runs of 4 pixels (W1 % 4 == 0) and two staging buffers of 16 streams next to a
+  // ring of maxh + 3 rows.  What it cannot take stays with the tiled kernel above.
+  PxGeom X = {};
+  CUtensorMap pxmap = pr.tmap, pxnb = pr.tmap;
+  bool strip = ctx->opt.volume_kernel != 1 && g.W1 % 4 == 0 && (reinterpret_cast<uintptr_t>(P.out) % 16) == 0;
+  size_t px_smem = 0;
+  if (strip) {
+    const BlockSchedule bs = g.bs;
+    const bool wide = bs.tail_r == kR;
+    X.WBs = kPxW - kP + bs.n8 * kR + (wide ? kNB : kP);
+    X.nb_off = (pr.CT * X.WBs + 31) & ~31;
+    X.pitch = dot ? X.nb_off + ((X.WBs + 31) & ~31) : X.nb_off;
+    X.nslot = maxh + kPxAhead;
+    X.nwide = bs.n8 + (wide ? 1 : 0);
+    const int rem = X.nwide % 4;
+    X.nbp = 2 * (X.nwide / 4) + (rem + 1) / 2;
+    // window rows in groups of four; one or two rows left over by a four-block-wide window (33 = 8 * 4 + 1)
+    // are one item of their own instead of a mostly idle group
+    X.nrow = (X.nwide == 4 && maxh >= 4 && (maxh % 4 == 1 || maxh % 4 == 2)) ? 1 : 0;
+    X.ndg = X.nrow ? maxh / 4 : (maxh + 3) / 4;
+    X.nfull = X.ndg * X.nbp;
+    X.items = X.nfull + X.nrow + (wide ? 0 : (maxh + 7) / 8);
+    X.strips = (g.W1 + kPxW - 1) / kPxW;
+    X.ncw = kPxMaxWarps;
+    {
+      auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+      X.rot = X.items;
+      while (gcd(X.rot, X.ncw) != 1) ++X.rot;
+    }
+    px_smem = ((size_t)X.nslot * X.pitch + 2 * (size_t)kPxW * K + 4 + (size_t)kPxARing * (pr.CT * kPxW + 2 * kPxW)) * sizeof(float) +
+              (2 * kPxMaxSlot + 6 + kPxARing) * sizeof(uint64_t);
+    strip = strip && X.WBs <= 256 && X.nslot <= kPxMaxSlot && X.nwide >= 1 && px_smem <= ctx->smem_optin;
+    // a step must hold enough items to keep the warps busy between two hand-overs: small windows (the
+    // multiscale 8x8: 3 items per step, measured 0.38 against 0.33 ms) stay with the tiled kernel
+    if (X.items < 2 * kPxMaxWarps && ctx->opt.volume_kernel != 2) strip = false;
+  }
+  if (strip) {
+    // rows per unit: the split of the strips into row bands that fills the CTAs' waves best (a unit
+    // pays about three steps for its first maxh - 1 rows)
+    const long long per_band = (long long)g.N * X.strips;
+    long long best = -1;
+    for (int nb = 1; nb <= g.H1 && nb <= 64; ++nb) {
+      const int band = (g.H1 + nb - 1) / nb;
+      if (band < 8 && nb > 1) break;
+      const long long waves = (per_band * nb + ctx->num_sms - 1) / ctx->num_sms;
+      const long long cost = waves * (band + 3);
+      if (best < 0 || cost < best) {
+        best = cost;
+        X.band = band;
+      }
+    }
+    X.nbands = (g.H1 + X.band - 1) / X.band;
+    X.units = (int)(per_band * X.nbands);
+    const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, (uint64_t)pr.Cin, (uint64_t)g.N};
+    const uint64_t strides[3] = {(uint64_t)pr.s2y * 4, (uint64_t)pr.s2c * 4, (uint64_t)pr.s2n * 4};
+    const uint32_t box[4] = {(uint32_t)X.WBs, 1u, (uint32_t)pr.CT, 1u};
+    DM_CHECK(tensor_map_4d(ctx, &pxmap, pr.in2_dev, dims, strides, box));
+    if (dot) {
+      const long long w2p = (g.W2 + 3) & ~3LL;
+      const uint64_t ndims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, 1u, (uint64_t)g.N};
+      const uint64_t nstr[3] = {(uint64_t)w2p * 4, (uint64_t)g.H2 * w2p * 4, (uint64_t)g.H2 * w2p * 4};
+      const uint32_t nbox[4] = {(uint32_t)X.WBs, 1u, 1u, 1u};
+      DM_CHECK(tensor_map_4d(ctx, &pxnb, nbuf_dev, ndims, nstr, nbox));
+    }
+  }
+  // soft-max volume on the strip kernel: minimum and sum are taken in the staging buffer, no statistics sweep
+  const bool fused_softmax = strip && mode == DM_VOLUME_NEG_SOFTMAX && !exact && K <= (size_t)kPxKRegs * 32 &&
+                             !(ctx->opt.volume_debug & 32);
+  if (mode == DM_VOLUME_NEG_SOFTMAX && !fused_softmax) {
     void *s = nullptr;
     DM_CHECK(call.alloc(&s, npx * 2 * sizeof(float)));
     float *vmin = static_cast<float *>(s), *vinv = vmin + npx;
@@ -1444,76 +1513,13 @@ int match_volume_on(Call &call, const dm_pair *in, int maxh, int maxw, int mode,
     count_launch(ctx);
     return DM_OK;
   };
-  // The strip kernel (match_volume_px.cuh) writes whole pixel streams with bulk copies; it needs
-  // 16-byte aligned runs of 4 pixels (W1 % 4 == 0) and two staging buffers of 16 streams next to a
-  // ring of maxh + 3 rows.  What it cannot take stays with the tiled kernel above.
-  PxGeom X = {};
-  CUtensorMap pxmap = pr.tmap, pxnb = pr.tmap;
-  bool strip = ctx->opt.volume_kernel != 1 && g.W1 % 4 == 0 && (reinterpret_cast<uintptr_t>(P.out) % 16) == 0;
-  size_t px_smem = 0;
-  if (strip) {
-    const BlockSchedule bs = g.bs;
-    const bool wide = bs.tail_r == kR;
-    X.WBs = kPxW - kP + bs.n8 * kR + (wide ? kNB : kP);
-    X.nb_off = (pr.CT * X.WBs + 31) & ~31;
-    X.pitch = dot ? X.nb_off + ((X.WBs + 31) & ~31) : X.nb_off;
-    X.nslot = maxh + kPxAhead;
-    X.nwide = bs.n8 + (wide ? 1 : 0);
-    const int rem = X.nwide % 4;
-    X.nbp = 2 * (X.nwide / 4) + (rem + 1) / 2;
-    // window rows in groups of four; one or two rows left over by a four-block-wide window (33 = 8 * 4 + 1)
-    // are one item of their own instead of a mostly idle group
-    X.nrow = (X.nwide == 4 && maxh >= 4 && (maxh % 4 == 1 || maxh % 4 == 2)) ? 1 : 0;
-    X.ndg = X.nrow ? maxh / 4 : (maxh + 3) / 4;
-    X.nfull = X.ndg * X.nbp;
-    X.items = X.nfull + X.nrow + (wide ? 0 : (maxh + 7) / 8);
-    X.strips = (g.W1 + kPxW - 1) / kPxW;
-    X.ncw = kPxMaxWarps;
-    {
-      auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
-      X.rot = X.items;
-      while (gcd(X.rot, X.ncw) != 1) ++X.rot;
-    }
-    px_smem = ((size_t)X.nslot * X.pitch + 2 * (size_t)kPxW * K + 4 + (size_t)kPxARing * (pr.CT * kPxW + 2 * kPxW)) * sizeof(float) +
-              (2 * kPxMaxSlot + 4 + kPxARing) * sizeof(uint64_t);
-    strip = strip && X.WBs <= 256 && X.nslot <= kPxMaxSlot && X.nwide >= 1 && px_smem <= ctx->smem_optin;
-    // a step must hold enough items to keep the warps busy between two hand-overs: small windows (the
-    // multiscale 8x8: 3 items per step, measured 0.38 against 0.33 ms) stay with the tiled kernel
-    if (X.items < 2 * kPxMaxWarps && ctx->opt.volume_kernel != 2) strip = false;
-  }
-  if (strip) {
-    // rows per unit: the split of the strips into row bands that fills the CTAs' waves best (a unit
-    // pays about three steps for its first maxh - 1 rows)
-    const long long per_band = (long long)g.N * X.strips;
-    long long best = -1;
-    for (int nb = 1; nb <= g.H1 && nb <= 64; ++nb) {
-      const int band = (g.H1 + nb - 1) / nb;
-      if (band < 8 && nb > 1) break;
-      const long long waves = (per_band * nb + ctx->num_sms - 1) / ctx->num_sms;
-      const long long cost = waves * (band + 3);
-      if (best < 0 || cost < best) {
-        best = cost;
-        X.band = band;
-      }
-    }
-    X.nbands = (g.H1 + X.band - 1) / X.band;
-    X.units = (int)(per_band * X.nbands);
-    const uint64_t dims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, (uint64_t)pr.Cin, (uint64_t)g.N};
-    const uint64_t strides[3] = {(uint64_t)pr.s2y * 4, (uint64_t)pr.s2c * 4, (uint64_t)pr.s2n * 4};
-    const uint32_t box[4] = {(uint32_t)X.WBs, 1u, (uint32_t)pr.CT, 1u};
-    DM_CHECK(tensor_map_4d(ctx, &pxmap, pr.in2_dev, dims, strides, box));
-    if (dot) {
-      const long long w2p = (g.W2 + 3) & ~3LL;
-      const uint64_t ndims[4] = {(uint64_t)g.W2, (uint64_t)g.H2, 1u, (uint64_t)g.N};
-      const uint64_t nstr[3] = {(uint64_t)w2p * 4, (uint64_t)g.H2 * w2p * 4, (uint64_t)g.H2 * w2p * 4};
-      const uint32_t nbox[4] = {(uint32_t)X.WBs, 1u, 1u, 1u};
-      DM_CHECK(tensor_map_4d(ctx, &pxnb, nbuf_dev, ndims, nstr, nbox));
-    }
-  }
   auto launch_px = [&](const VolumeParams &Q, int ssd_mode) -> int {
-#define DM_PICKX(ct)                                                                                      \
-  (ssd_mode == kExact ? (const void *)match_volume_px_kernel<ct, kExact>                                  \
-                      : (ssd_mode == kDot ? (const void *)match_volume_px_kernel<ct, kDot> : (const void *)match_volume_px_kernel<ct, kFma>))
+#define DM_PICKX(ct)                                                                                           \
+  (ssd_mode == kExact ? (const void *)match_volume_px_kernel<ct, kExact, false>                                \
+   : ssd_mode == kDot ? (fused_softmax ? (const void *)match_volume_px_kernel<ct, kDot, true>                  \
+                                       : (const void *)match_volume_px_kernel<ct, kDot, false>)                \
+                      : (fused_softmax ? (const void *)match_volume_px_kernel<ct, kFma, true>                  \
+                                       : (const void *)match_volume_px_kernel<ct, kFma, false>))
     const void *kfn = pr.CT == 4 ? DM_PICKX(4) : (pr.CT == 10 ? DM_PICKX(10) : DM_PICKX(16));
 #undef DM_PICKX
     DM_CHECK(ensure_func_smem(ctx, kfn, px_smem));

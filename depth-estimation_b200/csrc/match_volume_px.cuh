@@ -41,6 +41,7 @@ constexpr int kPxMaxWarps = 8;                     // compute warps (6 / 10 / 12
 constexpr int kPxMaxThreads = (kPxMaxWarps + 2) * 32;   // + TMA loader warp + store warp
 constexpr int kPxAhead = 3;                        // ring slots beyond the window height
 constexpr int kPxMaxSlot = 72;                     // barrier array size
+constexpr int kPxKRegs = 37;                       // fused soft-max: window entries per lane held in registers (K <= 1184)
 constexpr int kPxARing = 4;                        // steps of frame-1 values in flight (= kPxAhead + 1)
 
 struct PxGeom {
@@ -86,7 +87,60 @@ __device__ __forceinline__ void px_block_pair(int j, int nwide, int *b0, int *b1
   }
 }
 
-template <int CT, int MODE>
+// soft-max of two pixel streams of K floats in shared memory, in place, by one warp: values in registers
+// (K / 32 per lane and pixel; NF full chunks of 32 without a bounds test, the rest guarded), minimum and sum
+// by four partial chains + shuffles, one read and one write.  7 instructions per entry.
+template <int NF>
+__device__ __forceinline__ void px_softmax_two(float *base0, float *base1, int K, int lane) {
+  constexpr int NT = NF == 0 ? kPxKRegs : 3;          // guarded chunks after the NF full ones
+  float v0[NF + NT], v1[NF + NT];
+#pragma unroll
+  for (int j = 0; j < NF + NT; ++j) {
+    const int idx = lane + 32 * j;
+    const bool in = j < NF || idx < K;
+    v0[j] = in ? base0[idx] : 3.0e38f;
+    v1[j] = in ? base1[idx] : 3.0e38f;
+  }
+  float m0[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f}, m1[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+#pragma unroll
+  for (int j = 0; j < NF + NT; ++j) {
+    m0[j & 3] = fminf(m0[j & 3], v0[j]);
+    m1[j & 3] = fminf(m1[j & 3], v1[j]);
+  }
+  float a0 = fminf(fminf(m0[0], m0[1]), fminf(m0[2], m0[3])), a1 = fminf(fminf(m1[0], m1[1]), fminf(m1[2], m1[3]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 = fminf(a0, __shfl_xor_sync(0xffffffffu, a0, o));
+    a1 = fminf(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+  }
+  const float mL0 = a0 * kLog2e, mL1 = a1 * kLog2e;
+  float s0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, s1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int j = 0; j < NF + NT; ++j) {
+    // a padding value (3e38) gives ex2(-huge) = 0: no test needed here
+    v0[j] = ex2_approx(fmaf(v0[j], -kLog2e, mL0));
+    v1[j] = ex2_approx(fmaf(v1[j], -kLog2e, mL1));
+    s0[j & 3] += v0[j];
+    s1[j & 3] += v1[j];
+  }
+  float t0 = (s0[0] + s0[1]) + (s0[2] + s0[3]), t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+  }
+  const float i0 = 1.0f / t0, i1 = 1.0f / t1;
+#pragma unroll
+  for (int j = 0; j < NF + NT; ++j) {
+    const int idx = lane + 32 * j;
+    if (j < NF || idx < K) {
+      base0[idx] = v0[j] * i0;
+      base1[idx] = v1[j] * i1;
+    }
+  }
+}
+
+template <int CT, int MODE, bool FSM>
 __global__ void __launch_bounds__(kPxMaxThreads, 1)
 match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_nb,
                        const VolumeParams P, const PxGeom X) {
@@ -95,6 +149,10 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     if (dot_ok != (MODE == kDot)) return;
   }
   constexpr bool EXACT = MODE == kExact;
+  // FSM: soft-max volume without a statistics sweep -- the staging buffer holds the complete streams of the
+  // step's pixels, so minimum, sum and exp(min - v) / sum are taken there before the copy engine gets the
+  // buffer.  A template parameter: as a run-time flag its branches cost the plain SSD volume 7 %.
+  constexpr bool fused_softmax = FSM;
   const SweepGeom &g = P.g;
   const int maxh = g.maxh, maxw = g.maxw, K = maxh * maxw;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -104,7 +162,7 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
   constexpr int kAFloats = CT * kPxW + 2 * kPxW;
   float *aring = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(stage + 2 * (size_t)kPxW * K) + 15) & ~uintptr_t(15));
   uint64_t *full = reinterpret_cast<uint64_t *>(aring + kPxARing * kAFloats);
-  uint64_t *empty = full + kPxMaxSlot, *sdone = empty + kPxMaxSlot, *sfree = sdone + 2, *afull = sfree + 2;
+  uint64_t *empty = full + kPxMaxSlot, *sdone = empty + kPxMaxSlot, *sfree = sdone + 2, *afull = sfree + 2, *sraw = afull + kPxARing;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   constexpr int kPxWarps = kPxMaxWarps;   // compile-time: the item rotation and barrier counts fold
 
@@ -120,6 +178,7 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
       mbar_init(&sfree[b], 1);
     }
     for (int b = 0; b < kPxARing; ++b) mbar_init(&afull[b], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&sraw[b], kPxWarps);
     fence_mbar_init();
   }
   __syncthreads();
@@ -160,7 +219,7 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             } else if (idx < kAFloats) {
               const bool second = idx >= CT * kPxW + kPxW;
               t0 = second ? 1.0f : 0.0f;
-              if (P.mode == DM_VOLUME_NEG_SOFTMAX && x < g.W1)
+              if (P.mode == DM_VOLUME_NEG_SOFTMAX && !fused_softmax && x < g.W1)
                 t0 = second ? __ldg(P.vinv + orow + x) : __ldg(P.vmin + orow + x) * kLog2e;
             }
             v[e] = t0;
@@ -267,7 +326,7 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 ssd_block2<CT, EXACT, kR>(a2, brow, X.WBs, acc2);
               float acc[kP][kR];
               unpack_block<kR>(acc2, acc);
-              if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
+              if (P.mode == DM_VOLUME_NEG_SOFTMAX && !fused_softmax) {
 #pragma unroll
                 for (int p = 0; p < kP; ++p)
 #pragma unroll
@@ -298,7 +357,7 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 ssd_block2<CT, EXACT, 2>(a2, brow, X.WBs, acc2);
               float acc[kP][2];
               unpack_block<2>(acc2, acc);
-              if (P.mode == DM_VOLUME_NEG_SOFTMAX) {
+              if (P.mode == DM_VOLUME_NEG_SOFTMAX && !fused_softmax) {
 #pragma unroll
                 for (int p = 0; p < kP; ++p)
 #pragma unroll
@@ -320,6 +379,25 @@ match_volume_px_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
           fence_proxy_async();   // the staging stores of this thread -> visible to the copy engine
         }
         __syncwarp();
+        if constexpr (FSM) {
+          // soft-max volume without a statistics sweep: once every warp's entries of the step are in the buffer
+          // (sraw), warp w turns the streams of pixels 2w, 2w + 1 into probabilities in place.  Measured
+          // alternatives: three extra warps doing this under the next step's arithmetic are starved by the
+          // compute warps (0.61 ms); with the barrier the eight compute warps do it at full width
+          if (lane == 0) mbar_arrive(&sraw[b]);
+          mbar_wait(&sraw[b], use & 1u);
+          const int npx = min(kPxW, g.W1 - x0);
+          for (int px = 2 * warp; px < npx; px += 2 * kPxWarps) {
+            float *base0 = stage + (size_t)b * kPxW * K + (size_t)px * K;
+            float *base1 = px + 1 < npx ? base0 + K : base0;      // an odd last pixel is simply done twice
+            if (K >= 34 * 32 && K <= 37 * 32)
+              px_softmax_two<34>(base0, base1, K, lane);          // 33x33 and neighbours: 34 chunks unguarded
+            else
+              px_softmax_two<0>(base0, base1, K, lane);
+          }
+          fence_proxy_async();
+          __syncwarp();
+        }
         if (lane == 0) {
           mbar_arrive(&sdone[b]);
           // window row 0 of this step is not read again; the last step releases the rest

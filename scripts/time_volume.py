@@ -29,8 +29,13 @@ for kern in (0, 1, 2):
                 out = dm.match_volume(in1, f2, 33, 33, softmax=softmax, ctx=ctx)
                 ts.append(ctx.last_kernel_ms())
             t = min(ts[2:])
+            import time
+            torch.cuda.synchronize(); w0 = time.perf_counter()
+            for _ in range(10):
+                out = dm.match_volume(in1, f2, 33, 33, softmax=softmax, ctx=ctx)
+            torch.cuda.synchronize(); wall = (time.perf_counter() - w0) / 10 * 1e3
             print("kernel=%s stores=%s %-8s volume sweep ms: %s  -> %.2f TB/s" % (("strip", "tiled", "strip, difference form")[kern], ("on" if dbg == 0 else "off"),
-                  "softmax" if softmax else "ssd", " ".join("%.3f" % x for x in ts[2:]), nbytes / t / 1e9), flush=True)
+                  "softmax" if softmax else "ssd", " ".join("%.3f" % x for x in ts[2:]), nbytes / t / 1e9), "| whole call incl. allocation of the result: %.3f ms" % wall, flush=True)
             del out
 ctx.set_option("volume_debug", 0)
 ctx.set_option("volume_kernel", 0)

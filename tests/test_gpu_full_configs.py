@@ -213,7 +213,13 @@ def test_softmax_volume_of_a_large_call_vs_oracle(dm, oracle, data):
     ctx = dm.default_context()
     l0 = ctx.launch_count()
     got = dm.match_volume(in1, in2, maxh, maxw, softmax=True)
-    assert ctx.launch_count() - l0 == 6            # 2 norm passes + twin statistics + twin volume sweeps
+    assert ctx.launch_count() - l0 == 4            # 2 norm passes + twin strip kernels (soft-max in the staging buffer)
+    ctx.set_option("volume_kernel", 1)
+    l0 = ctx.launch_count()
+    two = dm.match_volume(in1, in2, maxh, maxw, softmax=True)
+    ctx.set_option("volume_kernel", 0)
+    assert ctx.launch_count() - l0 == 6            # tiled kernel: 2 norm passes + twin statistics + twin volume sweeps
+    np.testing.assert_allclose(got, two, rtol=2e-5, atol=1e-12)
     want = oracle.neg_softmax(oracle.spatial_matching(in1, in2, maxh, maxw))
     np.testing.assert_allclose(got, want.reshape(got.shape), rtol=1e-4, atol=1e-12)
     dif = dm.match_volume(in1 * 4, in2 * 4, maxh, maxw, softmax=True)      # norms beyond the bound: difference form

@@ -190,8 +190,11 @@ def test_volume_strip_kernel_vs_oracle_and_tiled_kernel(dm, oracle, case):
     np.testing.assert_array_equal(res[0][0], vol)
     np.testing.assert_allclose(res[0][1], vol, rtol=RTOL, atol=1e-6)
     np.testing.assert_allclose(res[0][2], prob, rtol=RTOL, atol=1e-9)
-    for a, b in zip(res[0], res[1]):
-        np.testing.assert_array_equal(a, b)
+    # same block functions in both kernels: the SSD volumes agree bit for bit; the strip kernel's soft-max
+    # takes min and sum in its staging buffer (another summation order than the statistics sweep)
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_allclose(res[0][2], res[1][2], rtol=2e-5, atol=1e-12)
 
 
 def test_volume_strip_kernel_many_units_per_cta(dm, oracle):
