@@ -208,6 +208,69 @@ static int fill_inputs(Call &call, const dm_pair *in, int maxh, int maxw, Generi
   return DM_OK;
 }
 
+// extractOutput on the RAW SSD volume (radial/radial_opticalflow_groundtruth.lua:105, version2/groundtruth.lua:103:
+// threshold 0.21 -> M = 4) without the volume: one warp per pixel walks the window in scan order, 32 entries at
+// a time, SSD with separately rounded multiply and add (the CPU path's arithmetic), keeps the FIRST M values
+// above the threshold with their 1-based positions (extract_output.cpp:96-114) and stops as soon as it has
+// them -- with a threshold below the typical SSD that is the first chunk.  Sorting network, ret and score as in
+// extract_output.cpp:17-61,123-129.  A pixel with no value above the threshold keeps ret = 0, score = 0 and is
+// counted (the reference leaves the caller's buffers untouched there).
+__global__ void __launch_bounds__(kGWarps * 32) raw_ssd_extract_kernel(const GenericParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long npx = (long long)P.N * P.H1 * P.W1;
+  const int K = P.maxh * P.maxw;
+  for (long long px = (long long)blockIdx.x * kGWarps + __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); px < npx;
+       px += (long long)gridDim.x * kGWarps) {
+    const int x = (int)(px % P.W1);
+    const int y = (int)((px / P.W1) % P.H1);
+    const int n = (int)(px / ((long long)P.W1 * P.H1));
+    const float *a = P.in1 + n * P.s1n + y * P.s1y + x;
+    const float *b0 = P.in2 + n * P.s2n + y * P.s2y + x;
+    float cval[8], cpos[8];
+    int got = 0;
+    for (int j = 0; j < 8; ++j) cval[j] = cpos[j] = 0.0f;
+    for (int k0 = 0; k0 < K && got < P.M; k0 += 32) {
+      const int k = k0 + lane;
+      float v = 0.0f;
+      if (k < K) {
+        const int dy = k / P.maxw, dx = k - dy * P.maxw;
+        v = ssd_at(P, a, b0 + dy * P.s2y + dx, true);
+      }
+      unsigned hit = __ballot_sync(0xffffffffu, k < K && (double)v > P.thr);
+      while (hit && got < P.M) {  // scan order: lower lanes are earlier entries
+        const int src = __ffs(hit) - 1;
+        hit &= hit - 1;
+        cval[got] = __shfl_sync(0xffffffffu, v, src);
+        cpos[got] = (float)(k0 + src + 1);
+        ++got;
+      }
+    }
+    if (lane != 0) continue;
+    long long ret = 0;
+    float score = 0.0f;
+    if (got > 0) {
+      const int nex = P.M == 4 ? 5 : 19;
+      for (int e = 0; e < nex; ++e) {
+        const int ia = P.M == 4 ? gNet4[e][0] : gNet8[e][0];
+        const int ib = P.M == 4 ? gNet4[e][1] : gNet8[e][1];
+        if (cval[ib] > cval[ia]) {
+          float t = cval[ia]; cval[ia] = cval[ib]; cval[ib] = t;
+          t = cpos[ia]; cpos[ia] = cpos[ib]; cpos[ib] = t;
+        }
+      }
+      ret = (long long)cpos[0];
+      for (int k = 1; k < P.M; ++k) cval[k] = __fadd_rn(cval[k], cval[k - 1]);
+      double acc = 0.0;
+      for (int k = 0; k < P.M; ++k) acc += (double)cval[k];
+      score = (float)acc;
+    } else if (P.n_untouched) {
+      atomicAdd(P.n_untouched + n, 1ull);
+    }
+    P.index_thr[px] = ret;
+    P.score_thr[px] = score;
+  }
+}
+
 static int launch_generic(dm_ctx *ctx, const GenericParams &P, bool volume) {
   const long long npx = (long long)P.N * P.H1 * P.W1;
   long long blocks = (npx + kGWarps - 1) / kGWarps;
@@ -347,4 +410,43 @@ extern "C" int dm_radial_match_extract(dm_ctx *ctx, const dm_pair *in, int h_win
     count_launch(ctx);
   }
   return call.finish();
+}
+
+namespace dm {
+static int raw_ssd_extract_on(Call &call, const dm_pair *in, int maxh, int maxw, double threshold, int64_t *ret,
+                              float *scores, int64_t *n_untouched) {
+  dm_ctx *ctx = call.ctx;
+  GenericParams P;
+  DM_CHECK(fill_inputs(call, in, maxh, maxw, &P));
+  const size_t npx = (size_t)P.N * P.H1 * P.W1;
+  P.thr = threshold;
+  P.M = threshold < 0.2 ? 8 : 4;
+  void *p = nullptr;
+  DM_CHECK(call.out(ret, npx * sizeof(long long), &p));
+  P.index_thr = static_cast<long long *>(p);
+  DM_CHECK(call.out(scores, npx * sizeof(float), &p));
+  P.score_thr = static_cast<float *>(p);
+  if (n_untouched) {
+    DM_CHECK(call.out(n_untouched, (size_t)P.N * 8, &p));
+    P.n_untouched = static_cast<unsigned long long *>(p);
+    DM_CUDA(cudaMemsetAsync(p, 0, (size_t)P.N * 8, ctx->stream));
+  }
+  long long blocks = ((long long)npx + kGWarps - 1) / kGWarps;
+  const long long cap = (long long)ctx->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  raw_ssd_extract_kernel<<<(int)blocks, kGWarps * 32, 0, ctx->stream>>>(P);
+  DM_CUDA(cudaGetLastError());
+  count_launch(ctx);
+  return DM_OK;
+}
+}  // namespace dm
+
+extern "C" int dm_match_extract_raw_ssd(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, double threshold,
+                                        int64_t *ret, float *scores, int64_t *n_untouched) {
+  DM_REQUIRE(ctx && in && ret && scores, "dm_match_extract_raw_ssd: NULL argument");
+  DM_CUDA(cudaSetDevice(ctx->device));
+  dm::Call call(ctx);
+  const int rc = dm::raw_ssd_extract_on(call, in, maxh, maxw, threshold, ret, scores, n_untouched);
+  const int rf = call.finish();
+  return rc != DM_OK ? rc : rf;
 }

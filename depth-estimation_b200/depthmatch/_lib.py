@@ -67,6 +67,7 @@ SIGNATURES = {
     "dm_neg_softmax": (_I, [_P, _P, _L, _I, _P]),
     "dm_argmax_tie": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
     "dm_extract_output": (_I, [_P, _P, _I, _I, _I, _D, _P, _P, C.POINTER(_L)]),
+    "dm_match_extract_raw_ssd": (_I, [_P, _P, _I, _I, _D, _P, _P, _P]),
     "dm_extract_output_marginalized": (_I, [_P, _P, _I, _I, _I, _D, _D, _P, _P]),
     "dm_soft_mean": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "dm_marginal_x": (_I, [_P, _P, _L, _I, _I, _P]),

@@ -20,7 +20,7 @@ __all__ = [
     "DenseMatch", "processOutput", "getOutputConfidences", "getOutputConfidences2", "yx2xMulti",
     "x2yxMulti", "x2yxMulti2", "x2yxMultiNumber", "getModelMultiscale", "multiscaleLength",
     "getRMax", "getC2PMask", "getP2CMask", "cartesian2polar", "polar2cartesian", "getKOutput",
-    "getP2CMaskOF", "flow2depth", "match_extract", "match_volume", "round_lua",
+    "getP2CMaskOF", "flow2depth", "match_extract", "match_extract_raw_ssd", "match_volume", "round_lua",
     "postProcessImage", "enlargeMask", "radial", "computeDepthMapFromFlow",
     "Filter", "getFilter", "getRadialFilter", "getMultiscalePrefilter", "downsample", "multiscaleInputs",
 ]
@@ -220,6 +220,24 @@ def match_volume(in1, in2, maxh, maxw, softmax=False, exact=False, ctx=None):
     mode = (DM_VOLUME_NEG_SOFTMAX if softmax else DM_VOLUME_SSD) | (DM_VOLUME_EXACT if exact else 0)
     check(c._lib.dm_match_volume(c.handle, C.byref(p), maxh, maxw, mode, optr))
     return out[0] if single else out
+
+
+def match_extract_raw_ssd(in1, in2, maxh, maxw, threshold=0.21, ctx=None):
+    """extractOutput on the raw SSD volume without the volume: what the ground-truth generators compute
+    (radial/radial_opticalflow_groundtruth.lua:105, version2/groundtruth.lua:103).  Returns
+    (ret [N,]H1,W1 int64, scores [N,]H1,W1 float32, untouched pixels per pair)."""
+    args = _Args(ctx)
+    single = (in1.dim() if _is_torch(in1) else np.ndim(in1)) == 3
+    p, a, b = _pair_struct(args, in1, in2)
+    c = args.ctx_for(a, b)
+    rptr, ret = args.out((p.n_pairs, p.h1, p.w1), np.int64, like=a)
+    sptr, sc = args.out((p.n_pairs, p.h1, p.w1), np.float32, like=a)
+    nun = np.zeros((p.n_pairs,), np.int64)
+    check(c._lib.dm_match_extract_raw_ssd(c.handle, C.byref(p), maxh, maxw, float(threshold), rptr, sptr,
+                                          nun.ctypes.data))
+    if single:
+        return ret[0], sc[0], int(nun[0])
+    return ret, sc, nun
 
 
 def match_extract(in1, in2, maxh, maxw, tie_middle=True, exact=False, prob_threshold=0.11,

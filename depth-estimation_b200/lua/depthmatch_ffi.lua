@@ -33,6 +33,8 @@ int dm_argmax_tie(dm_ctx *ctx, const float *vol, int64_t rows, int k, int middle
                   int64_t *index, float *value);
 int dm_extract_output(dm_ctx *ctx, const float *input, int h, int w, int n, double threshold,
                       int64_t *ret, float *scores, int64_t *n_untouched);
+int dm_match_extract_raw_ssd(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, double threshold,
+                             int64_t *ret, float *scores, int64_t *n_untouched);
 int dm_extract_output_marginalized(dm_ctx *ctx, const float *input, int h, int w, int n,
                                    double threshold, double threshold_acc, int64_t *ret,
                                    int64_t *retgd);

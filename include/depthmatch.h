@@ -160,6 +160,13 @@ int dm_argmax_tie(dm_ctx *ctx, const float *vol, int64_t rows, int k, int middle
  * pointer, may be NULL) receives their count. */
 int dm_extract_output(dm_ctx *ctx, const float *input, int h, int w, int n, double threshold,
                       int64_t *ret, float *scores, int64_t *n_untouched);
+/* the same extractOutput applied to the RAW SSD volume of a frame pair, volume never materialised: what the
+ * ground-truth generators compute with `extractOutput(output, scores, 0.21, ret)` on the matcher's output
+ * (radial/radial_opticalflow_groundtruth.lua:105, version2/groundtruth.lua:103: M = 4, the first four SSDs
+ * above the threshold in scan order).  ret / scores: [n_pairs][h1][w1]; a pixel with no SSD above the
+ * threshold gets ret = 0, score = 0 and is counted in n_untouched ([n_pairs], may be NULL). */
+int dm_match_extract_raw_ssd(dm_ctx *ctx, const dm_pair *in, int maxh, int maxw, double threshold,
+                             int64_t *ret, float *scores, int64_t *n_untouched);
 /* extractoutput.extractOutputMarginalized (extract_output.cpp:157-255); retgd is zeroed */
 int dm_extract_output_marginalized(dm_ctx *ctx, const float *input, int h, int w, int n,
                                    double threshold, double threshold_acc, int64_t *ret,

@@ -144,7 +144,7 @@ def test_lua_ffi_cdef_matches_the_header():
         assert params == h[name], (name, params, h[name])
     # everything a Lua host needs for the path itself is declared
     for name in ("dm_create", "dm_destroy", "dm_last_error", "dm_match_volume", "dm_match_extract",
-                 "dm_extract_output", "dm_x2yx_multi", "dm_cascade_add", "dm_multiscale_extract",
+                 "dm_extract_output", "dm_match_extract_raw_ssd", "dm_x2yx_multi", "dm_cascade_add", "dm_multiscale_extract",
                  "dm_polar_remap", "dm_flow2depth", "dm_filter_create", "dm_filter_forward",
                  "dm_post_process_image", "dm_enlarge_mask", "dm_warp_homography"):
         assert name in l, name

@@ -216,6 +216,35 @@ def test_volume_strip_kernel_many_units_per_cta(dm, oracle):
         np.testing.assert_allclose(gotp[n], oracle.neg_softmax(vol), rtol=RTOL, atol=1e-9)
 
 
+@pytest.mark.parametrize("case", [(10, 30, 150, 9, 17, 0.21, 0.5), (3, 19, 23, 4, 5, 0.21, 0.05), (10, 24, 40, 7, 7, 0.15, 0.1),
+                                  (20, 16, 20, 3, 4, 0.21, 0.02)])
+def test_raw_ssd_thresholded_extraction_vs_oracle(dm, oracle, case):
+    """extractOutput(volume of raw SSDs, 0.21) as the ground-truth generators call it
+    (radial/radial_opticalflow_groundtruth.lua:105, version2/groundtruth.lua:103), fused: no volume.  Oracle =
+    the reference's extract_output.cpp (restated, and the compiled original where built) on the oracle's volume.
+    Small noise keeps some SSDs under the threshold, so the scan has to pass over them; bit-exact."""
+    C, H2, W2, maxh, maxw, thr, noise = case
+    in1, in2, _ = make_pair(C, H2, W2, maxh, maxw, seed=9, noise=noise)
+    vol = oracle.spatial_matching(in1, in2, maxh, maxw)
+    K = maxh * maxw
+    want_ret, want_sc, written = oracle.extract_output(vol.reshape(vol.shape[0], vol.shape[1], K), thr)
+    ret, sc, untouched = dm.match_extract_raw_ssd(in1, in2, maxh, maxw, thr)
+    np.testing.assert_array_equal(ret, want_ret)
+    np.testing.assert_array_equal(sc, want_sc)
+    assert untouched == int((want_ret == 0).sum())
+    below = (vol.reshape(-1, K)[:, :8] <= thr).any()
+    if noise <= 0.05:
+        assert below      # the case really has entries the scan must skip
+    # batched device call
+    import torch
+    t1 = torch.from_numpy(np.stack([in1, in1])).cuda()
+    t2 = torch.from_numpy(np.stack([in2, in2])).cuda()
+    r2, s2, u2 = dm.match_extract_raw_ssd(t1, t2, maxh, maxw, thr)
+    np.testing.assert_array_equal(r2[1].cpu().numpy(), want_ret)
+    np.testing.assert_array_equal(s2[0].cpu().numpy(), want_sc)
+    assert list(u2) == [untouched, untouched]
+
+
 def test_module_level_process_output_vs_oracle(dm, oracle):
     """getModel(prefiltered) -> forward -> processOutput for 'max', 'max'+threshold and 'mean'."""
     maxh, maxw = 9, 9
