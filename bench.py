@@ -22,6 +22,8 @@ oracle (outside the timed region); `hard_data` repeats the measurement on unrela
 NCCL gather, strong scaling) at the same N.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -229,10 +231,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, the image's setting) goes
-        # to stdout too, so it is switched off unless the caller asked for real NCCL logging
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -668,4 +666,19 @@ def bench_row_bands(dm, dm_parallel, dist, rank, world, ctx, pairs=12, warmup=3)
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries exactly one JSON line.  Libraries write there too (NCCL's version banner comes through
+    # C stdio, whatever NCCL_DEBUG_FILE says), so file descriptor 1 points at stderr while the bench runs and
+    # the line goes to the real stdout at the end.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(_buf):
+            main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        os.close(_real_stdout)
+        sys.stdout.write(_buf.getvalue())
+        sys.stdout.flush()
