@@ -56,7 +56,11 @@ namespace dm {
 struct Options {
   int ssd_form = 0;  // 0 auto, 1 difference form always, 2 dot form whatever the norms
   bool no_small_tiles = false, no_pipeline = false, debug_todo = false;
-  int pipe_chunk = 0, volume_debug = 0;
+  int pipe_chunk = 0;
+  // tuning only (results may be wrong): volume kernels 1 = no global stores; strip kernel 32 = soft-max volume
+  // through the statistics sweep instead of the staging buffer; two-row sweep: its own bits (match_sweep2.cuh);
+  // 9 = role cycle counts of the tensor-core filter kernel on stderr
+  int volume_debug = 0;
   int conv_tile = 0, conv_target = 0;
   int sweep = 0;     // 0 auto; other values select a sweep variant (tuning)
   int volume_kernel = 0;  // 0 auto (strip kernel where it fits and pays), 1 = tiled kernel with sector stores, 2 = strip kernel wherever it fits

@@ -197,6 +197,37 @@ def test_volume_strip_kernel_vs_oracle_and_tiled_kernel(dm, oracle, case):
     np.testing.assert_allclose(res[0][2], res[1][2], rtol=2e-5, atol=1e-12)
 
 
+def test_volume_strip_kernel_writes_only_its_output(dm):
+    """Bulk copies of whole pixel streams: guard words before and after the caller's buffer stay untouched
+    (partial last strip, several pairs, both volume modes) and the result equals the ordinary call's."""
+    import ctypes
+    import torch
+    from depthmatch import _lib as dml
+    from depthmatch import api
+    rng = np.random.default_rng(21)
+    N, C, maxh, maxw = 2, 10, 9, 17
+    H1, W1 = 20, 136
+    H2, W2 = H1 + maxh - 1, W1 + maxw - 1
+    t2 = torch.from_numpy(rng.standard_normal((N, C, H2, W2), dtype=np.float32)).cuda()
+    t1 = (t2[:, :, 4:4 + H1, 8:8 + W1] + 0.2).contiguous()
+    ctx = dm.default_context()
+    ctx.set_option("volume_kernel", 2)
+    K, G = maxh * maxw, 4096
+    n_out = N * H1 * W1 * K
+    pr = dml.dm_pair()
+    pr.in1, pr.in2 = t1.data_ptr(), t2.data_ptr()
+    pr.n_pairs, pr.channels, pr.h1, pr.w1, pr.h2, pr.w2 = N, C, H1, W1, H2, W2
+    for mode, softmax in ((dml.DM_VOLUME_SSD, False), (dml.DM_VOLUME_NEG_SOFTMAX, True)):
+        buf = torch.full((G + n_out + G,), -12345.0, device="cuda")
+        api.check(ctx._lib.dm_match_volume(ctx.handle, ctypes.byref(pr), maxh, maxw, mode,
+                                           ctypes.c_void_p(buf.data_ptr() + 4 * G)))
+        torch.cuda.synchronize()
+        assert bool((buf[:G] == -12345.0).all()) and bool((buf[G + n_out:] == -12345.0).all())
+        want = dm.match_volume(t1, t2, maxh, maxw, softmax=softmax)
+        assert torch.equal(buf[G:G + n_out].view(want.shape), want)
+    ctx.set_option("volume_kernel", 0)
+
+
 def test_volume_strip_kernel_many_units_per_cta(dm, oracle):
     """More units than SMs (barrier phases carried across units), a partial last strip and row bands."""
     import torch
