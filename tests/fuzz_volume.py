@@ -15,7 +15,13 @@ bad = 0
 for case in range(n_cases):
     C = int(rng.choice([1, 3, 4, 7, 10, 16, 19]))
     maxh, maxw = int(rng.integers(1, 18)), int(rng.integers(1, 18))
+    if case % 4 == 3:   # large windows: the shapes the strip kernel is the default for (many items per step)
+        maxh, maxw = [(33, 33), (32, 32), (34, 33), (21, 40), (30, 17), (17, 65), (35, 31), (33, 34)][(case // 4) % 8]
     H2, W2 = int(rng.integers(maxh + 1, maxh + 30)), int(rng.integers(maxw + 1, maxw + 140))
+    strip = bool(rng.random() < 0.5)      # the strip kernel (whole pixel streams, bulk copies) wherever it fits
+    if strip:
+        W2 += (-(W2 - maxw + 1)) % 4      # it needs W1 % 4 == 0
+    dm.default_context().set_option("volume_kernel", 2 if strip else 0)
     in1, in2, _ = make_pair(C, H2, W2, maxh, maxw, seed=int(rng.integers(1 << 30)), noise=float(rng.choice([0, 0.3])))
     exact = bool(rng.random() < 0.5)
     vol = O.spatial_matching(in1, in2, maxh, maxw)
@@ -30,9 +36,10 @@ for case in range(n_cases):
     gp = dm.match_volume(in1, in2, maxh, maxw, softmax=True, exact=exact)
     if not np.allclose(gp, prob, rtol=1e-4, atol=1e-9):
         errs.append("softmax")
-    print("volume case %2d C=%2d win=%2dx%2d in2=%3dx%3d exact=%d: %s"
-          % (case, C, maxh, maxw, H2, W2, exact, "ok" if not errs else "FAIL " + ",".join(errs)), flush=True)
+    print("volume case %2d C=%2d win=%2dx%2d in2=%3dx%3d exact=%d strip=%d: %s"
+          % (case, C, maxh, maxw, H2, W2, exact, strip, "ok" if not errs else "FAIL " + ",".join(errs)), flush=True)
     bad += bool(errs)
+dm.default_context().set_option("volume_kernel", 0)
 for case in range(n_cases // 2):
     n_in, n_out = int(rng.integers(1, 9)), int(rng.integers(1, 13))
     kh, kw = int(rng.integers(1, 18)), int(rng.integers(1, 18))
