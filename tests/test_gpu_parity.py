@@ -171,7 +171,8 @@ def test_volume_ssd_and_softmax_vs_oracle(dm, oracle, case):
 
 
 @pytest.mark.parametrize("case", [(10, 30, 152, 9, 17), (4, 12, 100, 5, 33), (10, 20, 71, 8, 8), (16, 40, 64, 33, 33),
-                                  (3, 26, 44, 17, 9), (10, 21, 40, 4, 25)])
+                                  (3, 26, 44, 17, 9), (10, 21, 40, 4, 25), (4, 9, 12, 9, 9), (10, 5, 20, 4, 17),
+                                  (1, 3, 10, 1, 3), (10, 34, 36, 33, 33)])
 def test_volume_strip_kernel_vs_oracle_and_tiled_kernel(dm, oracle, case):
     """W1 % 4 == 0: the strip kernel (whole pixel streams, bulk copies; match_volume_px.cuh).  Against the
     oracle, and bit for bit against the tiled kernel (option volume_kernel = 1)."""
