@@ -225,3 +225,28 @@ def test_softmax_volume_of_a_large_call_vs_oracle(dm, oracle, data):
     dif = dm.match_volume(in1 * 4, in2 * 4, maxh, maxw, softmax=True)      # norms beyond the bound: difference form
     want = oracle.neg_softmax(oracle.spatial_matching(in1 * 4, in2 * 4, maxh, maxw))
     np.testing.assert_allclose(dif, want.reshape(dif.shape), rtol=1e-4, atol=1e-12)
+
+
+def test_volume_mode_north_full_pair_vs_oracle(dm, oracle):
+    """Volume mode (nn.SpatialMatching's output, then Minus + SoftMax) at the benchmarked size: one whole
+    640x360 / 33x33 pair, 869 MB per volume, through the strip kernel (bulk-copied pixel streams; soft-max taken in
+    its staging buffer) -- every entry against the oracle: SSD bit-exact in exact mode, 1e-4 otherwise."""
+    import torch
+    maxh = maxw = 33
+    in1, in2 = _pair(10, 360, 640, maxh, maxw, "0.05", 1234)
+    vol = oracle.spatial_matching(in1, in2, maxh, maxw)
+    t1, t2 = torch.from_numpy(in1).cuda(), torch.from_numpy(in2).cuda()
+    ctx = dm.default_context()
+    l0 = ctx.launch_count()
+    got = dm.match_volume(t1, t2, maxh, maxw, exact=True)
+    assert ctx.launch_count() - l0 == 1                      # one strip kernel, nothing else
+    assert torch.equal(got.cpu(), torch.from_numpy(vol).view(got.shape))
+    got = dm.match_volume(t1, t2, maxh, maxw)
+    np.testing.assert_allclose(got.cpu().numpy().reshape(vol.shape), vol, rtol=1e-4, atol=1e-5)
+    del got
+    prob = oracle.neg_softmax(vol)
+    del vol
+    l0 = ctx.launch_count()
+    gp = dm.match_volume(t1, t2, maxh, maxw, softmax=True)
+    assert ctx.launch_count() - l0 == 4                      # norm pre-pass (2) + twin strip kernels: no statistics sweep
+    np.testing.assert_allclose(gp.cpu().numpy().reshape(prob.shape), prob, rtol=1e-4, atol=1e-12)
